@@ -1,0 +1,115 @@
+/* wvd.h -- C ABI of libwvd.so: the B200-native (sm_100a) kernels behind the Wan2.1(-VACE) video-DiT denoising
+ * forward of Ditto/Editto (wangshiwen-ai-hku/video-styler).
+ *
+ * Boundary rules:
+ *   - plain extern "C"; no torch / ATen / pybind types.  Loaded with ctypes.
+ *   - every function returns int: 0 = OK, < 0 = error code; text via wvd_last_error() (thread-local).
+ *   - all buffers are caller-owned DEVICE pointers; no hidden allocation, no hidden synchronisation;
+ *     every launch takes the caller's cudaStream_t (pass torch.cuda.current_stream().cuda_stream).
+ *   - activations are row-major (tokens, channels) with an explicit leading dimension in ELEMENTS,
+ *     so views into fused buffers (e.g. the q|k|v buffer) need no copy.
+ *   - dtype enum: WVD_BF16 (storage bf16, math fp32) or WVD_F32.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef WVD_H_
+#define WVD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* wvd_stream_t; /* cudaStream_t */
+
+enum { WVD_OK = 0, WVD_ERR_INVALID = -1, WVD_ERR_CUDA = -2, WVD_ERR_UNSUPPORTED = -3 };
+enum { WVD_BF16 = 0, WVD_F32 = 1 };
+
+/* GEMM epilogues.  y = A.W^T + bias (fp32 accumulate, rounded to the storage dtype like F.linear).       */
+enum {
+    WVD_EPI_BIAS = 0,          /* C = y                                   nn.Linear (wan_video_dit.py:131-134) */
+    WVD_EPI_BIAS_GELU = 1,     /* C = gelu_tanh(y)                        ffn.0 + nn.GELU('tanh') (:209-210)    */
+    WVD_EPI_BIAS_RES = 2,      /* C = residual + y                        x + cross_attn(...) (:227); before_proj(c)+x (wan_video_vace.py:15) */
+    WVD_EPI_BIAS_GATE_RES = 3  /* C = residual + gate[n] * y              GateModule (:189-194, :226, :229)     */
+};
+
+/* ---- library info / diagnostics ------------------------------------------------------------------- */
+const char* wvd_last_error(void);
+int wvd_version(void);          /* 10000*major + 100*minor + patch */
+int wvd_sm_arch(void);          /* 100: the only architecture this library is compiled for (sm_100a) */
+/* Test hook: synchronises the device, copies out and clears the in-kernel watchdog record
+ * (out[0] = number of mbarrier waits that timed out, out[1] = tag of the last one, out[2] = block, out[3] = thread). */
+int wvd_debug_flags(unsigned long long out[8]);
+
+/* ---- K1/K2: LayerNorm (+ AdaLN modulate) ------------------------------------------------------------
+ * out = LN(x) * (1 + scale) + shift            (weight == bias == NULL; shift/scale of length dim)
+ * out = LN(x) * weight + bias                  (shift == scale == NULL)
+ * Replaces nn.LayerNorm + modulate(): wan_video_dit.py:64-65, 206-208, 225, 227, 228; Head.forward :262-269.
+ * Statistics in fp32, biased variance.  In bf16 mode the intermediate roundings of the reference's eager
+ * bf16 expression (LN -> bf16, (1+scale) -> bf16, product -> bf16, sum -> bf16) are reproduced.           */
+int wvd_ln_modulate(const void* x, int64_t ldx, const void* shift, const void* scale, const void* weight,
+                    const void* bias, void* out, int64_t ldo, int64_t n_tokens, int dim, float eps, int dtype,
+                    wvd_stream_t stream);
+
+/* ---- K3/K4: full-width RMSNorm of q and k (+ 3-D RoPE) ------------------------------------------------
+ * q <- rope(rmsnorm(q) * wq), k <- rope(rmsnorm(k) * wk); RMS over the whole hidden dim (all heads).
+ * Replaces RMSNorm.forward + rope_apply: wan_video_dit.py:92-111, 141-145, 177-178 and the rank-sliced twin
+ * diffsynth/distributed/xdit_context_parallel.py:27-40 (token_offset = rank * tokens_per_rank).
+ * rope_cs == NULL disables RoPE (cross-attention).  k == NULL processes q only.
+ * rope_cs: float2 (cos, sin) tables laid out [3][1024][32]: axis 0 = frame (22 pairs used), 1 = height (21),
+ * 2 = width (21) -- the reference's complex128 tables (wan_video_dit.py:75-89) cast to fp32.
+ * Token n (global index token_offset + local row) sits at (f, h, w) = (n / (gh*gw), (n / gw) % gh, n % gw);
+ * frame_ids (int32[gf], may be NULL) replaces f by frame_ids[f] (rope_indices, wan_video_dit.py:378-384).
+ * q_out/k_out may alias q/k.  head_dim must be 128.                                                      */
+int wvd_qk_rmsnorm_rope(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* wq, const void* wk,
+                        void* q_out, int64_t ldqo, void* k_out, int64_t ldko, int64_t n_tokens, int dim,
+                        int head_dim, float eps, const void* rope_cs, const int32_t* frame_ids, int grid_f,
+                        int grid_h, int grid_w, int64_t token_offset, int dtype, wvd_stream_t stream);
+
+/* ---- elementwise residual forms that are not fused into a GEMM epilogue -------------------------------
+ * out = x + y * scale   (VACE hint injection, diffsynth/pipelines/wan_video_new.py:1445-1450)            */
+int wvd_scale_add(const void* x, const void* y, float scale, void* out, int64_t n_elems, int dtype,
+                  wvd_stream_t stream);
+/* out = x + gate[c] * y (GateModule, wan_video_dit.py:189-194) -- only used when the producer is not a GEMM */
+int wvd_gate_residual(const void* x, const void* gate, const void* y, void* out, int64_t n_tokens, int dim,
+                      int dtype, wvd_stream_t stream);
+
+/* ---- K5-K7, K10: dense contraction on tcgen05 / TMEM, TMA-fed -----------------------------------------
+ * C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias[N]); A, W, C, residual bf16 row-major with leading dims
+ * lda/ldw/ldc/ldr (elements, multiples of 8); bias/gate bf16 vectors of length N (bias may be NULL).
+ * Replaces F.linear call sites wan_video_dit.py:131-134, 157-160, 209-210 and wan_video_vace.py:15,21.   */
+int wvd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
+                  int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue, const void* gate,
+                  const void* residual, int64_t ldr, wvd_stream_t stream);
+
+/* ---- K8/K9: flash-style attention forward, head_dim 128, non-causal, no mask ---------------------------
+ * out[s, h*128:(h+1)*128] = softmax(q_h k_h^T * scale) v_h ; q/k/v/out are (tokens, heads*128) bf16 views with
+ * leading dims in elements.  Replaces flash_attention(): wan_video_dit.py:28-61 (self: sq == sk; cross: sk = 512). */
+int wvd_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                      void* out, int64_t ldo, int num_heads, int64_t sq, int64_t sk, int head_dim, float scale,
+                      wvd_stream_t stream);
+
+/* ---- fp32 fall-through kernels (fp32 mode of the parity contract; CUDA-core math, not tuned) ----------- */
+int wvd_gemm_f32(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc,
+                 int64_t M, int64_t N, int64_t K, int epilogue, const void* gate, const void* residual,
+                 int64_t ldr, wvd_stream_t stream);
+int wvd_attention_fwd_f32(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                          void* out, int64_t ldo, int num_heads, int64_t sq, int64_t sk, int head_dim, float scale,
+                          wvd_stream_t stream);
+
+/* ---- C1: Ulysses layout helpers (diffsynth/distributed/xdit_context_parallel.py:110-131) ---------------
+ * pack:   qkv (n_local, 3*heads*128) [q|k|v]  ->  send (P, n_local, 3, heads/P, 128)  (dest-rank major)
+ *         after all-to-all the receive buffer is (P*n_local, 3*(heads/P)*128): q|k|v views with ld = 3*(heads/P)*128.
+ * The attention output (P*n_local, (heads/P)*128) is already the return-trip send layout; after the second
+ * all-to-all the buffer (P, n_local, (heads/P)*128) is consumed by unpack -> (n_local, heads*128).          */
+int wvd_ulysses_pack_qkv(const void* qkv, int64_t ld, void* send, int64_t n_local, int heads, int head_dim,
+                         int world, wvd_stream_t stream);
+int wvd_ulysses_unpack_out(const void* recv, void* out, int64_t ldo, int64_t n_local, int heads, int head_dim,
+                           int world, wvd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WVD_H_ */

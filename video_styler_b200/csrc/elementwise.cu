@@ -1,0 +1,461 @@
+// K1-K4 and the unfused residual forms: HBM-bound, vectorised (16-byte) kernels, one warp per token row.
+// A row (<= 6144 bf16 channels) is read once into registers, reduced with warp shuffles (no block barrier),
+// and written once: algorithmic traffic = 1 read + 1 write per element.
+//
+//   wvd_ln_modulate      LayerNorm (+ AdaLN modulate or affine)         wan_video_dit.py:64-65,206-208,225-228,262-269
+//   wvd_qk_rmsnorm_rope  full-width RMSNorm(q,k) * weight (+ 3-D RoPE)  wan_video_dit.py:92-111,141-145,177-178
+//   wvd_scale_add        x + y*scale (VACE hint injection)             wan_video_new.py:1445-1450
+//   wvd_gate_residual    x + gate*y                                    wan_video_dit.py:189-194
+//   wvd_ulysses_*        all-to-all send/receive layouts               distributed/xdit_context_parallel.py:110-131
+//
+// In bf16 mode every intermediate rounding of the reference's eager bf16 expressions is reproduced
+// (see the comments at each site), so the kernels are drop-in at the bit level up to fp32 reduction order.
+#include "host_utils.h"
+#include "ptx.cuh"
+
+namespace wvd {
+namespace ew {
+
+template <typename T> struct VecIO;
+
+template <> struct VecIO<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* f) {
+        uint4 u;
+        u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+        u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+    static __device__ __forceinline__ float rnd(float x) { return bf16_round(x); }
+};
+
+template <> struct VecIO<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const float* p, float* f) {
+        const float4 u = *reinterpret_cast<const float4*>(p);
+        f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float* f) {
+        *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+    static __device__ __forceinline__ float rnd(float x) { return x; }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+constexpr int WARPS_PER_BLOCK = 8;
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm + modulate / affine
+// ------------------------------------------------------------------------------------------------
+template <typename T, int MAXV, bool MODULATE, bool AFFINE>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+ln_modulate_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__ shift, const T* __restrict__ scale,
+                   const T* __restrict__ weight, const T* __restrict__ bias, T* __restrict__ out, long long ldo,
+                   long long n_tokens, int dim, float eps) {
+    using IO = VecIO<T>;
+    constexpr int VE = IO::N;
+    const int lane = threadIdx.x & 31;
+    const long long row = static_cast<long long>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (row >= n_tokens) return;
+    const int nvec = dim / VE;
+    const T* xr = x + row * ldx;
+    float v[MAXV][VE];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) {
+            IO::load(xr + vi * VE, v[i]);
+#pragma unroll
+            for (int e = 0; e < VE; ++e) sum += v[i][e];
+        }
+    }
+    const float mean = warp_sum(sum) / dim;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) {
+#pragma unroll
+            for (int e = 0; e < VE; ++e) { const float d = v[i][e] - mean; sq += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / dim + eps);
+    T* orow = out + row * ldo;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) {
+            float o[VE];
+            if (AFFINE) {
+                // F.layer_norm(x, weight, bias): ((x - mean) * rstd) * w + b in fp32, one rounding
+                float w[VE], b[VE];
+                IO::load(weight + vi * VE, w);
+                IO::load(bias + vi * VE, b);
+#pragma unroll
+                for (int e = 0; e < VE; ++e) o[e] = (v[i][e] - mean) * rstd * w[e] + b[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < VE; ++e) o[e] = IO::rnd((v[i][e] - mean) * rstd);       // LN output -> dtype
+            }
+            if (MODULATE) {
+                // modulate(): x * (1 + scale) + shift evaluated in the tensor dtype (wan_video_dit.py:64-65)
+                float sc[VE], sh[VE];
+                IO::load(scale + vi * VE, sc);
+                IO::load(shift + vi * VE, sh);
+#pragma unroll
+                for (int e = 0; e < VE; ++e) {
+                    if (AFFINE) o[e] = IO::rnd(o[e]);
+                    const float one_plus = IO::rnd(1.0f + sc[e]);
+                    o[e] = IO::rnd(o[e] * one_plus) + sh[e];
+                }
+            }
+            IO::store(orow + vi * VE, o);
+        }
+    }
+}
+
+template <typename T, int MAXV>
+int launch_ln(const void* x, int64_t ldx, const void* shift, const void* scale, const void* weight, const void* bias,
+              void* out, int64_t ldo, int64_t n, int dim, float eps, cudaStream_t s) {
+    const unsigned grid = static_cast<unsigned>((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    const dim3 block(WARPS_PER_BLOCK * 32);
+    const bool mod = shift != nullptr, aff = weight != nullptr;
+#define WVD_LN_LAUNCH(M, A)                                                                                      \
+    ln_modulate_kernel<T, MAXV, M, A><<<grid, block, 0, s>>>((const T*)x, ldx, (const T*)shift, (const T*)scale, \
+                                                             (const T*)weight, (const T*)bias, (T*)out, ldo, n, dim, eps)
+    if (mod && aff) WVD_LN_LAUNCH(true, true);
+    else if (mod) WVD_LN_LAUNCH(true, false);
+    else if (aff) WVD_LN_LAUNCH(false, true);
+    else WVD_LN_LAUNCH(false, false);
+#undef WVD_LN_LAUNCH
+    WVD_CHECK_CUDA(cudaGetLastError());
+    return WVD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm(q), RMSNorm(k) over the full hidden dim, * weight, then 3-D RoPE on adjacent channel pairs
+// ------------------------------------------------------------------------------------------------
+template <typename T, int MAXV, bool ROPE>
+__device__ __forceinline__ void rms_rope_row(const T* __restrict__ xr, const T* __restrict__ w, T* __restrict__ orow,
+                                             int dim, float eps, int lane, const float2* cs /*[VE/2]*/) {
+    using IO = VecIO<T>;
+    constexpr int VE = IO::N;
+    const int nvec = dim / VE;
+    float v[MAXV][VE];
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) {
+            IO::load(xr + vi * VE, v[i]);
+#pragma unroll
+            for (int e = 0; e < VE; ++e) sq += v[i][e] * v[i][e];
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / dim + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) {
+            float ww[VE], o[VE];
+            IO::load(w + vi * VE, ww);
+#pragma unroll
+            for (int e = 0; e < VE; ++e)   // norm(x.float()).to(dtype) * weight  (wan_video_dit.py:109-111)
+                o[e] = IO::rnd(IO::rnd(v[i][e] * rstd) * ww[e]);
+            if (ROPE) {
+#pragma unroll
+                for (int pr = 0; pr < VE / 2; ++pr) {   // (re, im) * (cos + i sin)  (wan_video_dit.py:92-97)
+                    const float re = o[2 * pr], im = o[2 * pr + 1];
+                    o[2 * pr] = re * cs[pr].x - im * cs[pr].y;
+                    o[2 * pr + 1] = re * cs[pr].y + im * cs[pr].x;
+                }
+            }
+            IO::store(orow + vi * VE, o);
+        }
+    }
+}
+
+template <typename T, int MAXV, bool ROPE>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+qk_rmsnorm_rope_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ k, long long ldk,
+                       const T* __restrict__ wq, const T* __restrict__ wk, T* __restrict__ qo, long long ldqo,
+                       T* __restrict__ ko, long long ldko, long long n_tokens, int dim, float eps,
+                       const float2* __restrict__ rope_cs, const int* __restrict__ frame_ids, int gh, int gw,
+                       long long token_offset) {
+    constexpr int VE = VecIO<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long long row = static_cast<long long>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (row >= n_tokens) return;
+    float2 cs[VE / 2];
+    if (ROPE) {
+        // this lane always owns the same pairs of every head: channel (lane*VE) % 128 (+ 0..VE-1)
+        const long long n = token_offset + row;
+        const int pw = static_cast<int>(n % gw);
+        const int ph = static_cast<int>((n / gw) % gh);
+        int pf = static_cast<int>(n / (static_cast<long long>(gw) * gh));
+        if (frame_ids != nullptr) pf = frame_ids[pf];
+        const int pair0 = ((lane * VE) % 128) / 2;
+#pragma unroll
+        for (int pr = 0; pr < VE / 2; ++pr) {
+            const int j = pair0 + pr;
+            int axis, jj, pos;
+            if (j < 22) { axis = 0; jj = j; pos = pf; }
+            else if (j < 43) { axis = 1; jj = j - 22; pos = ph; }
+            else { axis = 2; jj = j - 43; pos = pw; }
+            cs[pr] = __ldg(rope_cs + (static_cast<long long>(axis) * 1024 + pos) * 32 + jj);
+        }
+    }
+    rms_rope_row<T, MAXV, ROPE>(q + row * ldq, wq, qo + row * ldqo, dim, eps, lane, cs);
+    if (k != nullptr) rms_rope_row<T, MAXV, ROPE>(k + row * ldk, wk, ko + row * ldko, dim, eps, lane, cs);
+}
+
+template <typename T, int MAXV>
+int launch_rms(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* wq, const void* wk, void* qo,
+               int64_t ldqo, void* ko, int64_t ldko, int64_t n, int dim, float eps, const void* rope_cs,
+               const int32_t* frame_ids, int gh, int gw, int64_t token_offset, cudaStream_t s) {
+    const unsigned grid = static_cast<unsigned>((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    const dim3 block(WARPS_PER_BLOCK * 32);
+    if (rope_cs != nullptr)
+        qk_rmsnorm_rope_kernel<T, MAXV, true><<<grid, block, 0, s>>>(
+            (const T*)q, ldq, (const T*)k, ldk, (const T*)wq, (const T*)wk, (T*)qo, ldqo, (T*)ko, ldko, n, dim, eps,
+            (const float2*)rope_cs, frame_ids, gh, gw, token_offset);
+    else
+        qk_rmsnorm_rope_kernel<T, MAXV, false><<<grid, block, 0, s>>>(
+            (const T*)q, ldq, (const T*)k, ldk, (const T*)wq, (const T*)wk, (T*)qo, ldqo, (T*)ko, ldko, n, dim, eps,
+            nullptr, nullptr, 1, 1, 0);
+    WVD_CHECK_CUDA(cudaGetLastError());
+    return WVD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual forms
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+scale_add_kernel(const T* __restrict__ x, const T* __restrict__ y, float scale, T* __restrict__ out, long long nvec) {
+    using IO = VecIO<T>;
+    constexpr int VE = IO::N;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float a[VE], b[VE];
+        IO::load(x + i * VE, a);
+        IO::load(y + i * VE, b);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) a[e] = a[e] + IO::rnd(b[e] * scale);   // x + hint * vace_scale
+        IO::store(out + i * VE, a);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gate_residual_kernel(const T* __restrict__ x, const T* __restrict__ gate, const T* __restrict__ y, T* __restrict__ out,
+                     long long n_tokens, int dim) {
+    using IO = VecIO<T>;
+    constexpr int VE = IO::N;
+    const int vpr = dim / VE;
+    const long long nvec = n_tokens * vpr;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % vpr);
+        float a[VE], b[VE], g[VE];
+        IO::load(x + i * VE, a);
+        IO::load(y + i * VE, b);
+        IO::load(gate + c * VE, g);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) a[e] = a[e] + IO::rnd(g[e] * b[e]);
+        IO::store(out + i * VE, a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ulysses layouts (bf16, 16-byte vectors)
+// ------------------------------------------------------------------------------------------------
+// send[dest][row][which][hl][c] = qkv[row][which*H*hd + (dest*Hl + hl)*hd + c]
+__global__ void __launch_bounds__(256)
+ulysses_pack_kernel(const uint4* __restrict__ qkv, long long ld_vec, uint4* __restrict__ send, long long n_local,
+                    int heads, int hd_vec, int world) {
+    const int hl_n = heads / world;
+    const long long per_row = 3ll * hl_n * hd_vec;                  // vectors per (dest,row)
+    const long long total = static_cast<long long>(world) * n_local * per_row;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % hd_vec);
+        long long t = i / hd_vec;
+        const int hl = static_cast<int>(t % hl_n); t /= hl_n;
+        const int which = static_cast<int>(t % 3); t /= 3;
+        const long long row = t % n_local;
+        const int dest = static_cast<int>(t / n_local);
+        const long long src = row * ld_vec + (static_cast<long long>(which) * heads + dest * hl_n + hl) * hd_vec + c;
+        send[i] = qkv[src];
+    }
+}
+
+// out[row][src*Dl + c] = recv[src][row][c]
+__global__ void __launch_bounds__(256)
+ulysses_unpack_kernel(const uint4* __restrict__ recv, uint4* __restrict__ out, long long ldo_vec, long long n_local,
+                      int dl_vec, int world) {
+    const long long total = static_cast<long long>(world) * n_local * dl_vec;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % dl_vec);
+        long long t = i / dl_vec;
+        const long long row = t % n_local;
+        const int src = static_cast<int>(t / n_local);
+        out[row * ldo_vec + static_cast<long long>(src) * dl_vec + c] = recv[i];
+    }
+}
+
+inline unsigned stream_grid(long long work_items, int block) {
+    long long g = (work_items + block - 1) / block;
+    const long long cap = static_cast<long long>(sm_count()) * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<unsigned>(g);
+}
+
+}  // namespace ew
+}  // namespace wvd
+
+using namespace wvd;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" __attribute__((visibility("default"))) int wvd_ln_modulate(const void* x, int64_t ldx, const void* shift, const void* scale, const void* weight,
+                               const void* bias, void* out, int64_t ldo, int64_t n_tokens, int dim, float eps,
+                               int dtype, wvd_stream_t stream) {
+    WVD_REQUIRE(x && out, "wvd_ln_modulate: null pointer");
+    WVD_REQUIRE((shift == nullptr) == (scale == nullptr), "wvd_ln_modulate: shift and scale go together");
+    WVD_REQUIRE((weight == nullptr) == (bias == nullptr), "wvd_ln_modulate: weight and bias go together");
+    WVD_REQUIRE(dtype == WVD_BF16 || dtype == WVD_F32, "wvd_ln_modulate: bad dtype %d", dtype);
+    const int ve = dtype == WVD_BF16 ? 8 : 4;
+    WVD_REQUIRE(dim > 0 && dim % ve == 0 && ldx % ve == 0 && ldo % ve == 0 && ldx >= dim && ldo >= dim,
+                "wvd_ln_modulate: dim/ld must be multiples of %d (dim=%d)", ve, dim);
+    WVD_REQUIRE(aligned16(x) && aligned16(out) && aligned16(shift) && aligned16(scale) && aligned16(weight) && aligned16(bias),
+                "wvd_ln_modulate: pointers must be 16-byte aligned");
+    if (n_tokens == 0) return WVD_OK;
+    WVD_REQUIRE(n_tokens > 0, "wvd_ln_modulate: negative n_tokens");
+    const int nvec = dim / ve;
+    const int need = (nvec + 31) / 32;
+    cudaStream_t s = (cudaStream_t)stream;
+#define WVD_DISPATCH(T)                                                                                             \
+    if (need <= 2) return ew::launch_ln<T, 2>(x, ldx, shift, scale, weight, bias, out, ldo, n_tokens, dim, eps, s);     \
+    if (need <= 6) return ew::launch_ln<T, 6>(x, ldx, shift, scale, weight, bias, out, ldo, n_tokens, dim, eps, s);     \
+    if (need <= 12) return ew::launch_ln<T, 12>(x, ldx, shift, scale, weight, bias, out, ldo, n_tokens, dim, eps, s);   \
+    if (need <= 20) return ew::launch_ln<T, 20>(x, ldx, shift, scale, weight, bias, out, ldo, n_tokens, dim, eps, s);   \
+    if (need <= 40) return ew::launch_ln<T, 40>(x, ldx, shift, scale, weight, bias, out, ldo, n_tokens, dim, eps, s);
+    if (dtype == WVD_BF16) { WVD_DISPATCH(__nv_bfloat16) } else { WVD_DISPATCH(float) }
+#undef WVD_DISPATCH
+    return set_error(WVD_ERR_UNSUPPORTED, "wvd_ln_modulate: dim %d too large", dim);
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_qk_rmsnorm_rope(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* wq,
+                                   const void* wk, void* q_out, int64_t ldqo, void* k_out, int64_t ldko,
+                                   int64_t n_tokens, int dim, int head_dim, float eps, const void* rope_cs,
+                                   const int32_t* frame_ids, int grid_f, int grid_h, int grid_w, int64_t token_offset,
+                                   int dtype, wvd_stream_t stream) {
+    WVD_REQUIRE(q && wq && q_out, "wvd_qk_rmsnorm_rope: null pointer");
+    WVD_REQUIRE(k == nullptr || (wk && k_out), "wvd_qk_rmsnorm_rope: k needs wk and k_out");
+    WVD_REQUIRE(dtype == WVD_BF16 || dtype == WVD_F32, "wvd_qk_rmsnorm_rope: bad dtype %d", dtype);
+    WVD_REQUIRE(head_dim == 128, "wvd_qk_rmsnorm_rope: head_dim must be 128 (got %d)", head_dim);
+    const int ve = dtype == WVD_BF16 ? 8 : 4;
+    WVD_REQUIRE(dim > 0 && dim % head_dim == 0 && ldq % ve == 0 && ldqo % ve == 0 && ldq >= dim && ldqo >= dim,
+                "wvd_qk_rmsnorm_rope: bad dim/ld");
+    if (k) WVD_REQUIRE(ldk % ve == 0 && ldko % ve == 0 && ldk >= dim && ldko >= dim, "wvd_qk_rmsnorm_rope: bad k ld");
+    WVD_REQUIRE(aligned16(q) && aligned16(k) && aligned16(wq) && aligned16(wk) && aligned16(q_out) && aligned16(k_out),
+                "wvd_qk_rmsnorm_rope: pointers must be 16-byte aligned");
+    if (n_tokens == 0) return WVD_OK;
+    WVD_REQUIRE(n_tokens > 0, "wvd_qk_rmsnorm_rope: negative n_tokens");
+    if (rope_cs) {
+        WVD_REQUIRE(grid_f > 0 && grid_h > 0 && grid_w > 0 && grid_h <= 1024 && grid_w <= 1024,
+                    "wvd_qk_rmsnorm_rope: bad token grid %dx%dx%d", grid_f, grid_h, grid_w);
+        WVD_REQUIRE(token_offset >= 0 && token_offset + n_tokens <= (int64_t)grid_f * grid_h * grid_w,
+                    "wvd_qk_rmsnorm_rope: tokens [%lld,%lld) exceed the %dx%dx%d grid", (long long)token_offset,
+                    (long long)(token_offset + n_tokens), grid_f, grid_h, grid_w);
+        WVD_REQUIRE(frame_ids != nullptr || grid_f <= 1024, "wvd_qk_rmsnorm_rope: more than 1024 frames");
+    }
+    const int need = (dim / ve + 31) / 32;
+    cudaStream_t s = (cudaStream_t)stream;
+#define WVD_DISPATCH(T)                                                                                                \
+    if (need <= 2) return ew::launch_rms<T, 2>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_h, grid_w, token_offset, s);   \
+    if (need <= 6) return ew::launch_rms<T, 6>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_h, grid_w, token_offset, s);   \
+    if (need <= 12) return ew::launch_rms<T, 12>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_h, grid_w, token_offset, s); \
+    if (need <= 20) return ew::launch_rms<T, 20>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_h, grid_w, token_offset, s); \
+    if (need <= 40) return ew::launch_rms<T, 40>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_h, grid_w, token_offset, s);
+    if (dtype == WVD_BF16) { WVD_DISPATCH(__nv_bfloat16) } else { WVD_DISPATCH(float) }
+#undef WVD_DISPATCH
+    return set_error(WVD_ERR_UNSUPPORTED, "wvd_qk_rmsnorm_rope: dim %d too large", dim);
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_scale_add(const void* x, const void* y, float scale, void* out, int64_t n_elems, int dtype,
+                             wvd_stream_t stream) {
+    WVD_REQUIRE(dtype == WVD_BF16 || dtype == WVD_F32, "wvd_scale_add: bad dtype %d", dtype);
+    if (n_elems == 0) return WVD_OK;
+    WVD_REQUIRE(x && y && out && n_elems > 0, "wvd_scale_add: null pointer");
+    const int ve = dtype == WVD_BF16 ? 8 : 4;
+    WVD_REQUIRE(n_elems % ve == 0, "wvd_scale_add: n_elems must be a multiple of %d", ve);
+    WVD_REQUIRE(aligned16(x) && aligned16(y) && aligned16(out), "wvd_scale_add: pointers must be 16-byte aligned");
+    const long long nvec = n_elems / ve;
+    const unsigned grid = ew::stream_grid(nvec, 256);
+    if (dtype == WVD_BF16)
+        ew::scale_add_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, scale, (__nv_bfloat16*)out, nvec);
+    else
+        ew::scale_add_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)y, scale, (float*)out, nvec);
+    WVD_CHECK_CUDA(cudaGetLastError());
+    return WVD_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_gate_residual(const void* x, const void* gate, const void* y, void* out, int64_t n_tokens, int dim,
+                                 int dtype, wvd_stream_t stream) {
+    WVD_REQUIRE(dtype == WVD_BF16 || dtype == WVD_F32, "wvd_gate_residual: bad dtype %d", dtype);
+    if (n_tokens == 0) return WVD_OK;
+    WVD_REQUIRE(x && gate && y && out && n_tokens > 0, "wvd_gate_residual: null pointer");
+    const int ve = dtype == WVD_BF16 ? 8 : 4;
+    WVD_REQUIRE(dim > 0 && dim % ve == 0, "wvd_gate_residual: dim must be a multiple of %d", ve);
+    WVD_REQUIRE(aligned16(x) && aligned16(y) && aligned16(out) && aligned16(gate), "wvd_gate_residual: alignment");
+    const long long nvec = n_tokens * (dim / ve);
+    const unsigned grid = ew::stream_grid(nvec, 256);
+    if (dtype == WVD_BF16)
+        ew::gate_residual_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gate, (const __nv_bfloat16*)y, (__nv_bfloat16*)out, n_tokens, dim);
+    else
+        ew::gate_residual_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)gate, (const float*)y, (float*)out, n_tokens, dim);
+    WVD_CHECK_CUDA(cudaGetLastError());
+    return WVD_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_ulysses_pack_qkv(const void* qkv, int64_t ld, void* send, int64_t n_local, int heads, int head_dim,
+                                    int world, wvd_stream_t stream) {
+    WVD_REQUIRE(world >= 1 && heads > 0 && heads % world == 0, "wvd_ulysses_pack_qkv: heads (%d) must divide by world (%d)", heads, world);
+    WVD_REQUIRE(head_dim % 8 == 0 && ld % 8 == 0 && ld >= 3ll * heads * head_dim, "wvd_ulysses_pack_qkv: bad head_dim/ld");
+    if (n_local == 0) return WVD_OK;
+    WVD_REQUIRE(qkv && send && n_local > 0 && aligned16(qkv) && aligned16(send), "wvd_ulysses_pack_qkv: bad pointers");
+    const long long total = (long long)n_local * 3 * heads * (head_dim / 8);
+    ew::ulysses_pack_kernel<<<ew::stream_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)qkv, ld / 8, (uint4*)send, n_local, heads, head_dim / 8, world);
+    WVD_CHECK_CUDA(cudaGetLastError());
+    return WVD_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_ulysses_unpack_out(const void* recv, void* out, int64_t ldo, int64_t n_local, int heads,
+                                      int head_dim, int world, wvd_stream_t stream) {
+    WVD_REQUIRE(world >= 1 && heads > 0 && heads % world == 0, "wvd_ulysses_unpack_out: heads (%d) must divide by world (%d)", heads, world);
+    WVD_REQUIRE(head_dim % 8 == 0 && ldo % 8 == 0 && ldo >= (int64_t)heads * head_dim, "wvd_ulysses_unpack_out: bad head_dim/ld");
+    if (n_local == 0) return WVD_OK;
+    WVD_REQUIRE(recv && out && n_local > 0 && aligned16(recv) && aligned16(out), "wvd_ulysses_unpack_out: bad pointers");
+    const int dl_vec = (heads / world) * head_dim / 8;
+    const long long total = (long long)world * n_local * dl_vec;
+    ew::ulysses_unpack_kernel<<<ew::stream_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)recv, (uint4*)out, ldo / 8, n_local, dl_vec, world);
+    WVD_CHECK_CUDA(cudaGetLastError());
+    return WVD_OK;
+}

@@ -1,0 +1,218 @@
+"""Tensor-level wrappers over the C ABI (include/wvd.h).  PyTorch supplies device memory and the stream only.
+
+All activations are 2-D row-major views (tokens, channels) whose last stride is 1; the row stride is passed as
+the leading dimension, so column slices of fused buffers (q|k|v) are used without copies.
+bf16 tensors run the tcgen05 kernels; fp32 tensors run the fp32 CUDA-core kernels (parity mode).  Anything else,
+or a CPU tensor, raises: the hot path has no fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_RES, WVD_BF16, WVD_F32, WvdError, check
+
+Tensor = torch.Tensor
+
+
+def _dt(t: Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return WVD_BF16
+    if t.dtype == torch.float32:
+        return WVD_F32
+    raise WvdError(f"unsupported dtype {t.dtype}: the wvd kernels take bfloat16 (tensor-core path) or float32 (parity mode)")
+
+
+def _chk2d(t: Tensor, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise WvdError(f"{name} is on {t.device}: the wvd hot path runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise WvdError(f"{name} must be a 2-D view with unit last stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t
+
+
+def _ld(t: Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _vec(t: Optional[Tensor], n: int, name: str, like: Tensor):
+    if t is None:
+        return None
+    t = t.reshape(-1)
+    if t.numel() != n or t.dtype != like.dtype or not t.is_cuda or t.stride(0) != 1:
+        raise WvdError(f"{name} must be a contiguous {like.dtype} CUDA vector of length {n}, got {tuple(t.shape)} {t.dtype}")
+    return t
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def as_2d(x: Tensor) -> Tensor:
+    """(1, N, D) or (N, D) -> (N, D) view."""
+    if x.dim() == 3:
+        if x.shape[0] != 1:
+            raise WvdError("batched activations must be looped over by the caller (batch 1 per call)")
+        return x[0]
+    return x
+
+
+def ln_modulate(x: Tensor, shift: Optional[Tensor] = None, scale: Optional[Tensor] = None,
+                weight: Optional[Tensor] = None, bias: Optional[Tensor] = None, eps: float = 1e-6,
+                out: Optional[Tensor] = None) -> Tensor:
+    """LN(x)*(1+scale)+shift, or LN(x)*weight+bias (wan_video_dit.py:64-65, 206-208)."""
+    x = _chk2d(x, "x")
+    n, d = x.shape
+    if out is None:
+        out = torch.empty((n, d), dtype=x.dtype, device=x.device)
+    _chk2d(out, "out")
+    shift, scale = _vec(shift, d, "shift", x), _vec(scale, d, "scale", x)
+    weight, bias = _vec(weight, d, "weight", x), _vec(bias, d, "bias", x)
+    check(_lib.load().wvd_ln_modulate(x.data_ptr(), _ld(x), _p(shift), _p(scale), _p(weight), _p(bias), out.data_ptr(),
+                                      _ld(out), n, d, eps, _dt(x), _stream()), "wvd_ln_modulate")
+    return out
+
+
+def make_rope_table(freqs: Tuple[Tensor, Tensor, Tensor], device) -> Tensor:
+    """The model's three complex128 tables (wan_video_dit.py:75-89) -> one fp32 (3, 1024, 32, 2) cos/sin table."""
+    tab = torch.zeros(3, 1024, 32, 2, dtype=torch.float32)
+    for a, f in enumerate(freqs):
+        n, w = f.shape
+        if n > 1024 or w > 32:
+            raise WvdError(f"rope table axis {a} has shape {tuple(f.shape)}; expected <= (1024, 32)")
+        tab[a, :n, :w, 0] = f.real.to(torch.float32)
+        tab[a, :n, :w, 1] = f.imag.to(torch.float32)
+    return tab.to(device).contiguous()
+
+
+def qk_rmsnorm_rope(q: Tensor, k: Optional[Tensor], wq: Tensor, wk: Optional[Tensor], eps: float,
+                    rope_table: Optional[Tensor] = None, grid: Tuple[int, int, int] = (1, 1, 1),
+                    token_offset: int = 0, frame_ids: Optional[Tensor] = None,
+                    q_out: Optional[Tensor] = None, k_out: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """q <- rope(rmsnorm(q)*wq), k likewise; in place unless q_out/k_out given (wan_video_dit.py:92-111,141-145)."""
+    q = _chk2d(q, "q")
+    n, d = q.shape
+    q_out = q if q_out is None else _chk2d(q_out, "q_out")
+    wq = _vec(wq, d, "norm_q.weight", q)
+    if k is not None:
+        k = _chk2d(k, "k")
+        if k.shape != q.shape or k.dtype != q.dtype:
+            raise WvdError("q and k must have the same shape/dtype (process the cross-attention k separately)")
+        k_out = k if k_out is None else _chk2d(k_out, "k_out")
+        wk = _vec(wk, d, "norm_k.weight", q)
+    if rope_table is not None:
+        if rope_table.dtype != torch.float32 or tuple(rope_table.shape) != (3, 1024, 32, 2) or not rope_table.is_cuda:
+            raise WvdError("rope_table must be the (3,1024,32,2) fp32 CUDA table from make_rope_table()")
+        if frame_ids is not None and (frame_ids.dtype != torch.int32 or not frame_ids.is_cuda):
+            raise WvdError("frame_ids must be an int32 CUDA tensor")
+    gf, gh, gw = grid
+    check(_lib.load().wvd_qk_rmsnorm_rope(
+        q.data_ptr(), _ld(q), _p(k), _ld(k) if k is not None else 0, wq.data_ptr(), _p(wk), q_out.data_ptr(), _ld(q_out),
+        _p(k_out) if k is not None else None, _ld(k_out) if k is not None else 0, n, d, 128, eps, _p(rope_table),
+        _p(frame_ids), gf, gh, gw, token_offset, _dt(q), _stream()), "wvd_qk_rmsnorm_rope")
+    return q_out, k_out
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, epilogue: int = EPI_BIAS,
+           gate: Optional[Tensor] = None, residual: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """out = epilogue(x @ weight.T + bias) -- F.linear with fused GELU-tanh / residual / gate*y + residual."""
+    x = _chk2d(x, "x")
+    weight = _chk2d(weight, "weight")
+    m, k = x.shape
+    n, k2 = weight.shape
+    if k2 != k or weight.dtype != x.dtype:
+        raise WvdError(f"linear: x {tuple(x.shape)} {x.dtype} vs weight {tuple(weight.shape)} {weight.dtype}")
+    if out is None:
+        out = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    _chk2d(out, "out")
+    if out.shape != (m, n):
+        raise WvdError(f"linear: out has shape {tuple(out.shape)}, expected {(m, n)}")
+    bias = _vec(bias, n, "bias", x)
+    gate = _vec(gate, n, "gate", x)
+    if residual is not None:
+        residual = _chk2d(residual, "residual")
+        if residual.shape != (m, n) or residual.dtype != x.dtype:
+            raise WvdError("linear: residual shape/dtype mismatch")
+    fn = _lib.load().wvd_gemm_bf16 if x.dtype == torch.bfloat16 else _lib.load().wvd_gemm_f32
+    _dt(x)
+    if m == 0:
+        return out
+    check(fn(x.data_ptr(), _ld(x), weight.data_ptr(), _ld(weight), _p(bias), out.data_ptr(), _ld(out), m, n, k, epilogue,
+             _p(gate), _p(residual), _ld(residual) if residual is not None else 0, _stream()), "wvd_gemm")
+    return out
+
+
+def attention(q: Tensor, k: Tensor, v: Tensor, num_heads: int, out: Optional[Tensor] = None,
+              scale: Optional[float] = None) -> Tensor:
+    """softmax(q k^T / sqrt(128)) v per head; q (Sq, H*128), k/v (Sk, H*128) views (wan_video_dit.py:28-61)."""
+    q, k, v = _chk2d(q, "q"), _chk2d(k, "k"), _chk2d(v, "v")
+    sq, width = q.shape
+    sk = k.shape[0]
+    if width != num_heads * 128 or k.shape[1] != width or v.shape != k.shape or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise WvdError(f"attention: head_dim must be 128 and q/k/v consistent (q {tuple(q.shape)}, k {tuple(k.shape)}, "
+                       f"v {tuple(v.shape)}, heads {num_heads})")
+    if out is None:
+        out = torch.empty((sq, width), dtype=q.dtype, device=q.device)
+    _chk2d(out, "out")
+    scale = 1.0 / math.sqrt(128.0) if scale is None else scale
+    fn = _lib.load().wvd_attention_fwd if q.dtype == torch.bfloat16 else _lib.load().wvd_attention_fwd_f32
+    _dt(q)
+    check(fn(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(), _ld(out), num_heads, sq,
+             sk, 128, scale, _stream()), "wvd_attention_fwd")
+    return out
+
+
+def scale_add(x: Tensor, y: Tensor, scale: float, out: Optional[Tensor] = None) -> Tensor:
+    """x + y*scale (VACE hint injection, wan_video_new.py:1445-1450).  Contiguous tensors of equal shape."""
+    if not (x.is_cuda and y.is_cuda) or x.shape != y.shape or x.dtype != y.dtype or not x.is_contiguous() or not y.is_contiguous():
+        raise WvdError("scale_add: x and y must be contiguous CUDA tensors of equal shape/dtype")
+    out = torch.empty_like(x) if out is None else out
+    check(_lib.load().wvd_scale_add(x.data_ptr(), y.data_ptr(), float(scale), out.data_ptr(), x.numel(), _dt(x), _stream()),
+          "wvd_scale_add")
+    return out
+
+
+def gate_residual(x: Tensor, gate: Tensor, y: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """x + gate*y (GateModule, wan_video_dit.py:189-194)."""
+    x, y = _chk2d(x, "x"), _chk2d(y, "y")
+    if not x.is_contiguous() or not y.is_contiguous() or x.shape != y.shape:
+        raise WvdError("gate_residual: contiguous x/y of equal shape required")
+    n, d = x.shape
+    gate = _vec(gate, d, "gate", x)
+    out = torch.empty_like(x) if out is None else out
+    check(_lib.load().wvd_gate_residual(x.data_ptr(), gate.data_ptr(), y.data_ptr(), out.data_ptr(), n, d, _dt(x), _stream()),
+          "wvd_gate_residual")
+    return out
+
+
+def ulysses_pack_qkv(qkv: Tensor, heads: int, world: int, out: Optional[Tensor] = None) -> Tensor:
+    """(n_local, 3*heads*128) [q|k|v] -> (world, n_local, 3, heads/world, 128): dest-rank-major all-to-all send buffer."""
+    qkv = _chk2d(qkv, "qkv")
+    n = qkv.shape[0]
+    if qkv.dtype != torch.bfloat16 or qkv.shape[1] != 3 * heads * 128:
+        raise WvdError("ulysses_pack_qkv: bf16 (n, 3*heads*128) expected")
+    if out is None:
+        out = torch.empty((world, n, 3, heads // world, 128), dtype=qkv.dtype, device=qkv.device)
+    check(_lib.load().wvd_ulysses_pack_qkv(qkv.data_ptr(), _ld(qkv), out.data_ptr(), n, heads, 128, world, _stream()),
+          "wvd_ulysses_pack_qkv")
+    return out
+
+
+def ulysses_unpack_out(recv: Tensor, heads: int, world: int, out: Optional[Tensor] = None) -> Tensor:
+    """(world, n_local, (heads/world)*128) -> (n_local, heads*128)."""
+    if recv.dtype != torch.bfloat16 or not recv.is_contiguous() or not recv.is_cuda:
+        raise WvdError("ulysses_unpack_out: contiguous bf16 CUDA tensor expected")
+    n = recv.shape[1]
+    if out is None:
+        out = torch.empty((n, heads * 128), dtype=recv.dtype, device=recv.device)
+    _chk2d(out, "out")
+    check(_lib.load().wvd_ulysses_unpack_out(recv.data_ptr(), out.data_ptr(), _ld(out), n, heads, 128, world, _stream()),
+          "wvd_ulysses_unpack_out")
+    return out
