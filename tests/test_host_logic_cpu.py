@@ -1,0 +1,155 @@
+"""Host-side logic without a GPU: the package's module tree (state-dict key parity with the reference), the
+engine/pipeline orchestration (driven through a CPU stand-in for the kernel wrappers) against the golden vectors
+from the REAL reference, the scheduler, and the loud failure when the CUDA path is unavailable."""
+import os
+
+import pytest
+import torch
+
+import video_styler_b200 as V
+from oracle import wan_oracle as O
+from tests import cpu_backend
+from video_styler_b200 import _lib, engine, ops
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+
+
+def build_models(fix, dtype=torch.float32, device="cpu"):
+    cfg = O.DIT_CONFIGS[fix["size"]]
+    dit = V.WanModel(has_image_input=False, **cfg)
+    sd = O.make_state_dict(O.dit_param_shapes(cfg), seed=fix["seeds"]["dit"], perturb_norms=fix["perturb"],
+                           weight_scale=fix["weight_scale"])
+    res = dit.load_state_dict(sd, strict=True)           # key names == the reference's state-dict keys
+    assert not res.missing_keys and not res.unexpected_keys
+    vace = None
+    if fix["with_vace"]:
+        vcfg = O.VACE_CONFIGS[fix["size"]]
+        vace = V.VaceWanModel(has_image_input=False, **vcfg)
+        vsd = O.make_state_dict(O.vace_param_shapes(vcfg), seed=fix["seeds"]["vace"], perturb_norms=fix["perturb"],
+                                weight_scale=fix["weight_scale"])
+        if fix["lora"]:
+            O.lora_merge(vsd, O.make_lora_state_dict(vcfg, seed=fix["seeds"]["lora"], rank=fix["lora_rank"]))
+        vace.load_state_dict(vsd, strict=True)
+        vace = vace.to(device=device, dtype=dtype).eval().requires_grad_(False)
+    return dit.to(device=device, dtype=dtype).eval().requires_grad_(False), vace
+
+
+def run_model_fn(fix, dit, vace, backend, device="cpu", dtype=torch.float32, **kw):
+    cfg = O.DIT_CONFIGS[fix["size"]]
+    inp = O.make_inputs(fix["latent_shape"], cfg["text_dim"], seed=fix["seeds"]["inputs"], with_vace=fix["with_vace"])
+    ts = torch.tensor([fix["timestep"]], dtype=torch.float32).to(device=device, dtype=dtype)
+    with torch.no_grad():
+        return V.model_fn_wan_video(dit=dit, vace=vace, latents=inp["latents"].to(device=device, dtype=dtype),
+                                    timestep=ts, context=inp["context"].to(device=device, dtype=dtype),
+                                    vace_context=inp["vace_context"].to(device=device, dtype=dtype) if fix["with_vace"] else None,
+                                    vace_scale=1.0, ops=backend, **kw)
+
+
+@pytest.mark.parametrize("name", ["tiny_t2v", "tiny_vace_lora", "small_vace"])
+def test_pipeline_orchestration_matches_reference_golden(golden_dir, name):
+    fix = _load(golden_dir, name)
+    dit, vace = build_models(fix)
+    out = run_model_fn(fix, dit, vace, cpu_backend)
+    m = O.parity_metrics(out, fix["output"])
+    assert m["max_abs"] <= 5e-5 and m["rel_l2"] <= 2e-5, m
+
+
+def test_state_dict_keys_match_reference_names():
+    cfg, vcfg = O.DIT_CONFIGS["tiny"], O.VACE_CONFIGS["tiny"]
+    assert set(V.WanModel(has_image_input=False, **cfg).state_dict()) == set(O.dit_param_shapes(cfg))
+    assert set(V.VaceWanModel(**vcfg).state_dict()) == set(O.vace_param_shapes(vcfg))
+    # GeneralLoRALoader walks named_modules() for 'vace_blocks.N.self_attn.q' ... (diffsynth/lora/__init__.py:31-42)
+    names = dict(V.VaceWanModel(**vcfg).named_modules())
+    for tgt in O.LORA_TARGETS:
+        assert isinstance(names[f"vace_blocks.1.{tgt}"], torch.nn.Linear)
+
+
+def test_state_dict_converters_infer_config():
+    cfg, vcfg = O.DIT_CONFIGS["1.3B"], O.VACE_CONFIGS["14B"]
+    shapes = O.dit_param_shapes(cfg)
+    meta = {k: torch.empty(v, device="meta") for k, v in shapes.items()}
+    meta["vace_patch_embedding.weight"] = torch.empty(1, device="meta")
+    sd, got = V.WanModel.state_dict_converter().from_civitai({"model.diffusion_model." + k if not k.startswith("vace") else k: v
+                                                              for k, v in meta.items()})
+    assert set(sd) == set(shapes)
+    for k in ("dim", "in_dim", "ffn_dim", "out_dim", "text_dim", "freq_dim", "num_heads", "num_layers", "patch_size"):
+        assert got[k] == cfg[k], k
+    vmeta = {k: torch.empty(v, device="meta") for k, v in O.vace_param_shapes(vcfg).items()}
+    vmeta["blocks.0.modulation"] = torch.empty(1, device="meta")
+    vsd, vgot = V.VaceWanModel.state_dict_converter().from_civitai(vmeta)
+    assert set(vsd) == set(O.vace_param_shapes(vcfg))
+    for k in ("vace_layers", "vace_in_dim", "dim", "num_heads", "ffn_dim"):
+        assert vgot[k] == vcfg[k], k
+
+
+def test_rope_indices_variant_matches_oracle():
+    """The fixed WanModel.forward(rope_indices=...) of wan_video_dit.py:378-384."""
+    fix = dict(size="tiny", seeds=dict(dit=0, vace=3, lora=2, inputs=1), perturb=True, weight_scale=1.0,
+               with_vace=False, lora=False, latent_shape=(1, 16, 3, 8, 12), timestep=700.0)
+    dit, _ = build_models(fix)
+    idx = torch.tensor([0, 7, 20])
+    out = run_model_fn(fix, dit, None, cpu_backend, rope_indices=idx)
+    cfg = O.DIT_CONFIGS["tiny"]
+    sd = O.make_state_dict(O.dit_param_shapes(cfg), seed=0, perturb_norms=True)
+    inp = O.make_inputs(fix["latent_shape"], cfg["text_dim"], seed=1)
+    with torch.no_grad():
+        ref = O.model_fn_wan_video(sd, cfg, inp["latents"], torch.tensor([700.0]), inp["context"], rope_indices=idx)
+    assert O.parity_metrics(out, ref)["max_abs"] <= 5e-5
+
+
+def test_scheduler_and_denoise_loop(golden_dir):
+    fix = _load(golden_dir, "flow_match")
+    sch = V.FlowMatchScheduler(shift=5, sigma_min=0.0, extra_one_step=True)
+    sch.set_timesteps(50, shift=5.0)
+    assert torch.equal(sch.sigmas, fix["sigmas"]) and torch.equal(sch.timesteps, fix["timesteps"])
+    for i, ref in fix["steps"].items():
+        assert torch.allclose(sch.step(fix["v"], sch.timesteps[i], fix["x"]), ref, atol=1e-6, rtol=0)
+    # 3-step CFG loop through the package vs the oracle's restatement of wan_video_new.py:515-542
+    f = dict(size="tiny", seeds=dict(dit=0, vace=3, lora=2, inputs=1), perturb=True, weight_scale=1.0,
+             with_vace=False, lora=False)
+    dit, _ = build_models(f)
+    cfg = O.DIT_CONFIGS["tiny"]
+    sd = O.make_state_dict(O.dit_param_shapes(cfg), seed=0, perturb_norms=True)
+    inp = O.make_inputs((1, 16, 3, 8, 12), cfg["text_dim"], seed=1)
+    nega = torch.zeros_like(inp["context"])
+    import functools
+    import video_styler_b200.pipeline as P
+    orig = P.model_fn_wan_video
+    P.model_fn_wan_video = functools.partial(orig, ops=cpu_backend)
+    try:
+        got = V.denoise(dit, None, inp["latents"], inp["context"], nega, num_inference_steps=3, cfg_scale=5.0,
+                        torch_dtype=torch.float32)
+    finally:
+        P.model_fn_wan_video = orig
+    with torch.no_grad():
+        ref = O.denoise_loop(lambda latents, timestep, context: O.model_fn_wan_video(sd, cfg, latents, timestep, context),
+                             inp["latents"], 3, 5.0, torch.float32, dict(context=inp["context"]), dict(context=nega))
+    assert O.parity_metrics(got, ref)["max_abs"] <= 1e-4
+
+
+def test_product_path_fails_loudly_without_cuda():
+    """No CPU fallback: CPU tensors (or a missing extension) raise instead of silently computing elsewhere."""
+    x = torch.randn(8, 256)
+    with pytest.raises(_lib.WvdError):
+        ops.ln_modulate(x, eps=1e-6)
+    with pytest.raises(_lib.WvdError):
+        ops.linear(x.bfloat16(), torch.randn(256, 256).bfloat16())
+    with pytest.raises(_lib.WvdError):
+        ops.attention(x.bfloat16(), x.bfloat16(), x.bfloat16(), 2)
+    fix = dict(size="tiny", seeds=dict(dit=0, vace=3, lora=2, inputs=1), perturb=True, weight_scale=1.0,
+               with_vace=False, lora=False, latent_shape=(1, 16, 3, 8, 12), timestep=700.0)
+    dit, _ = build_models(fix)
+    with pytest.raises(_lib.WvdError):
+        run_model_fn(fix, dit, None, ops)          # default backend on CPU tensors
+
+
+def test_unsupported_surface_raises():
+    fix = dict(size="tiny", seeds=dict(dit=0, vace=3, lora=2, inputs=1), perturb=True, weight_scale=1.0,
+               with_vace=False, lora=False, latent_shape=(1, 16, 3, 8, 12), timestep=700.0)
+    dit, _ = build_models(fix)
+    with pytest.raises(NotImplementedError):
+        run_model_fn(fix, dit, None, cpu_backend, clip_feature=torch.zeros(1))
+    with pytest.raises(NotImplementedError):
+        V.WanModel(has_image_input=True, **O.DIT_CONFIGS["tiny"])

@@ -1,0 +1,13 @@
+"""video_styler_b200 -- B200-native (sm_100a) Wan2.1(-VACE) DiT denoising forward for Ditto / Editto.
+
+Host code is Python/PyTorch (device memory, streams, torch.distributed); the math runs in libwvd.so, a C-ABI
+library of hand-written CUDA kernels (include/wvd.h).  Public surface mirrors the reference:
+
+    model_fn_wan_video, WanModel, VaceWanModel, FlowMatchScheduler, denoise, install(pipe)
+"""
+from ._lib import WvdError  # noqa: F401
+from .pipeline import FlowMatchScheduler, denoise, install, model_fn_wan_video  # noqa: F401
+from .wan_video_dit import WanModel  # noqa: F401
+from .wan_video_vace import VaceWanModel  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,209 @@
+"""Host-side orchestration of one DiT block / VACE block / head over the C-ABI kernels.
+
+Everything here is duck-typed on the reference's module tree (attribute names ``self_attn.q``, ``norm_q``,
+``modulation``, ``ffn[0]`` ...), so the same functions drive both this package's own modules
+(``wan_video_dit.WanModel``) and a reference ``diffsynth`` pipeline patched by ``install()``.
+Weights are fetched through ``_lin`` / ``_param`` which unwrap ``diffsynth.vram_management`` wrappers
+(``AutoWrappedModule.module``); nothing is copied or re-packed, so LoRA merges and ``load_state_dict`` keep working.
+
+Data layout: activations are (tokens, channels) row-major bf16 in HBM; the residual stream ``x`` is updated in
+place by the GEMM epilogues (o-proj: x += gate*y, cross o-proj: x += y, ffn.2: x += gate*y).
+q|k|v live in ONE (tokens, 3*D) buffer: three GEMMs write its column slices, the RMSNorm+RoPE kernel updates
+q and k in place, and the attention kernel reads the slices through strided TMA maps.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops as _cuda_ops
+
+Tensor = torch.Tensor
+
+
+@dataclass
+class RopeInfo:
+    """3-D RoPE addressing for the fused QK-RMSNorm+RoPE kernel (wan_video_new.py:1392-1396)."""
+    table: Tensor                      # (3, 1024, 32, 2) fp32 cos/sin
+    grid: Tuple[int, int, int]         # (f, h, w) token grid
+    token_offset: int = 0              # global index of local row 0 (Ulysses shard)
+    frame_ids: Optional[Tensor] = None  # int32 (f,) -- rope_indices (wan_video_dit.py:378-384)
+
+
+@dataclass
+class Workspace:
+    """Caller-owned scratch for one (tokens, dim, ffn) problem; reused by every block of every step, so the TMA
+    tensor-map cache inside libwvd.so always hits."""
+    n: int
+    dim: int
+    ffn: int
+    ctx_len: int
+    dtype: torch.dtype
+    device: torch.device
+    bufs: Dict[str, Tensor] = field(default_factory=dict)
+
+    def get(self, name: str, shape) -> Tensor:
+        t = self.bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=self.dtype, device=self.device)
+            self.bufs[name] = t
+        return t
+
+
+_workspaces: Dict[tuple, Workspace] = {}
+
+
+def workspace(n: int, dim: int, ffn: int, ctx_len: int, dtype, device) -> Workspace:
+    key = (n, dim, ffn, ctx_len, dtype, str(device))
+    ws = _workspaces.get(key)
+    if ws is None:
+        if len(_workspaces) > 8:
+            _workspaces.clear()
+        ws = Workspace(n, dim, ffn, ctx_len, dtype, torch.device(device))
+        _workspaces[key] = ws
+    return ws
+
+
+def _unwrap(m):
+    """diffsynth.vram_management.AutoWrappedModule keeps the real module in ``.module`` (layers.py:36-60)."""
+    inner = getattr(m, "module", None)
+    return inner if isinstance(inner, torch.nn.Module) and not hasattr(m, "weight") else m
+
+
+def _lin(m, dtype, device):
+    m = _unwrap(m)
+    w, b = m.weight, m.bias
+    if w.dtype != dtype or w.device != device:          # offloaded / differently typed weights: cast like AutoWrappedLinear
+        w = w.to(device=device, dtype=dtype)
+        b = None if b is None else b.to(device=device, dtype=dtype)
+    return w, b
+
+
+def _param(p, dtype, device):
+    if p.dtype != dtype or p.device != device:
+        p = p.to(device=device, dtype=dtype)
+    return p
+
+
+def _norm_w(m, dtype, device):
+    return _param(_unwrap(m).weight, dtype, device)
+
+
+def block_modulation(block, t_mod: Tensor) -> Tensor:
+    """(modulation + t_mod) -> (6, D) rows [shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp]
+    (wan_video_dit.py:218-219).  Per-token modulation (4-D t_mod, Wan2.2 TI2V) is not on this path."""
+    if t_mod.dim() != 3 or t_mod.shape[0] != 1:
+        raise NotImplementedError("per-token / batched t_mod (seperated_timestep) is not supported by the wvd path")
+    return (block.modulation.to(dtype=t_mod.dtype, device=t_mod.device) + t_mod)[0].contiguous()
+
+
+class SelfAttnExchange:
+    """Single-GPU: attention reads q|k|v in place.  ulysses.UlyssesExchange overrides this with the all-to-all."""
+    world = 1
+
+    def attend(self, ops, qkv: Tensor, heads: int, out: Tensor, ws: Workspace) -> Tensor:
+        d = heads * 128
+        return ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], heads, out=out)
+
+
+_LOCAL = SelfAttnExchange()
+
+
+def dit_block_forward(block, x: Tensor, context: Tensor, t_mod: Tensor, rope: RopeInfo, ws: Workspace,
+                      ops=_cuda_ops, exchange: SelfAttnExchange = _LOCAL) -> Tensor:
+    """DiTBlock.forward (wan_video_dit.py:214-230) on a (tokens, D) residual stream, updated IN PLACE.
+
+    context: (L_ctx, D) text embedding (already through dit.text_embedding)."""
+    dt, dev = x.dtype, x.device
+    n, d = x.shape
+    sa, ca = block.self_attn, block.cross_attn
+    heads = sa.num_heads
+    if getattr(ca, "has_image_input", False):
+        raise NotImplementedError("image-conditioned cross attention (k_img/v_img) is not on the wvd path")
+    eps = block.norm1.eps
+    mod = block_modulation(block, t_mod)
+    # ---- self attention: x += gate_msa * o(attn(rope(rms(q)), rope(rms(k)), v)) ----
+    h = ops.ln_modulate(x, mod[0], mod[1], eps=eps, out=ws.get("h", (n, d)))
+    qkv = ws.get("qkv", (n, 3 * d))
+    for i, proj in enumerate((sa.q, sa.k, sa.v)):
+        w, b = _lin(proj, dt, dev)
+        ops.linear(h, w, b, out=qkv[:, i * d:(i + 1) * d])
+    ops.qk_rmsnorm_rope(qkv[:, :d], qkv[:, d:2 * d], _norm_w(sa.norm_q, dt, dev), _norm_w(sa.norm_k, dt, dev),
+                        _unwrap(sa.norm_q).eps, rope.table, rope.grid, rope.token_offset, rope.frame_ids)
+    a = exchange.attend(ops, qkv, heads, ws.get("attn", (n, d)), ws)
+    w, b = _lin(sa.o, dt, dev)
+    ops.linear(a, w, b, ops.EPI_BIAS_GATE_RES, gate=mod[2], residual=x, out=x)
+    # ---- cross attention (ungated): x += o(attn(rms(q(norm3(x))), rms(k(ctx)), v(ctx))) ----
+    n3 = _unwrap(block.norm3)
+    h = ops.ln_modulate(x, weight=_param(n3.weight, dt, dev), bias=_param(n3.bias, dt, dev), eps=n3.eps,
+                        out=ws.get("h", (n, d)))
+    w, b = _lin(ca.q, dt, dev)
+    q = ops.linear(h, w, b, out=ws.get("qc", (n, d)))
+    ops.qk_rmsnorm_rope(q, None, _norm_w(ca.norm_q, dt, dev), None, _unwrap(ca.norm_q).eps)
+    lc = context.shape[0]
+    w, b = _lin(ca.k, dt, dev)
+    kc = ops.linear(context, w, b, out=ws.get("kc", (lc, d)))
+    ops.qk_rmsnorm_rope(kc, None, _norm_w(ca.norm_k, dt, dev), None, _unwrap(ca.norm_k).eps)
+    w, b = _lin(ca.v, dt, dev)
+    vc = ops.linear(context, w, b, out=ws.get("vc", (lc, d)))
+    a = ops.attention(q, kc, vc, heads, out=ws.get("attn", (n, d)))
+    w, b = _lin(ca.o, dt, dev)
+    ops.linear(a, w, b, ops.EPI_BIAS_RES, residual=x, out=x)
+    # ---- ffn: x += gate_mlp * W2 gelu_tanh(W1 modulate(norm2(x))) ----
+    h = ops.ln_modulate(x, mod[3], mod[4], eps=block.norm2.eps, out=ws.get("h", (n, d)))
+    w, b = _lin(block.ffn[0], dt, dev)
+    mid = ops.linear(h, w, b, ops.EPI_BIAS_GELU, out=ws.get("mid", (n, w.shape[0])))
+    w, b = _lin(block.ffn[2], dt, dev)
+    ops.linear(mid, w, b, ops.EPI_BIAS_GATE_RES, gate=mod[5], residual=x, out=x)
+    return x
+
+
+def head_forward(head, x: Tensor, t: Tensor, ws: Workspace, ops=_cuda_ops) -> Tensor:
+    """Head.forward (wan_video_dit.py:262-269): Linear(LN(x)*(1+scale)+shift), modulation + t (not t_mod)."""
+    if t.dim() != 2 or t.shape[0] != 1:
+        raise NotImplementedError("per-token head modulation (seperated_timestep) is not supported by the wvd path")
+    dt, dev = x.dtype, x.device
+    n, d = x.shape
+    m = (head.modulation.to(dtype=t.dtype, device=t.device) + t.unsqueeze(1))[0].contiguous()   # (2, D): shift, scale
+    h = ops.ln_modulate(x, m[0], m[1], eps=head.norm.eps, out=ws.get("h", (n, d)))
+    w, b = _lin(head.head, dt, dev)
+    return ops.linear(h, w, b, out=ws.get("head_out", (n, w.shape[0])))
+
+
+def vace_forward(vace, x: Tensor, vace_context: Tensor, context: Tensor, t_mod: Tensor, rope: RopeInfo,
+                 ws: Workspace, ops=_cuda_ops, exchange: SelfAttnExchange = _LOCAL,
+                 token_slice: Optional[slice] = None) -> Tensor:
+    """VaceWanModel.forward + VaceWanAttentionBlock.forward (wan_video_vace.py:13-24, 53-87).
+
+    Returns the hints as ONE preallocated (n_hints, tokens, D) buffer (the reference's O(k^2) stack/unbind copying
+    disappears): c0 = before_proj(patch(vc)) + x ; c_{k+1} = block_k(c_k) ; hint_k = after_proj_k(c_{k+1}).
+    x: (tokens, D) patch-embedded main stream (read only).  token_slice selects this rank's tokens (Ulysses)."""
+    dt, dev = x.dtype, x.device
+    n, d = x.shape
+    if vace_context.shape[0] != 1:
+        raise NotImplementedError("batched vace_context: loop over the batch in the caller")
+    pe = _unwrap(vace.vace_patch_embedding)
+    c = torch.nn.functional.conv3d(vace_context.to(dt), _param(pe.weight, dt, dev), _param(pe.bias, dt, dev),
+                                   stride=pe.stride)
+    c = c.flatten(2).transpose(1, 2)[0]                                     # (tokens_total, D)
+    if token_slice is not None:
+        c = c[token_slice]
+    if c.shape[0] > n:
+        raise ValueError("vace_context has more tokens than the latent grid")
+    c_buf = ws.get("vace_c", (n, d))
+    c_buf[:c.shape[0]].copy_(c)
+    if c.shape[0] < n:                                                      # zero-pad to len(x) (wan_video_vace.py:60-63)
+        c_buf[c.shape[0]:].zero_()
+    blocks = vace.vace_blocks
+    hints = ws.get("vace_hints", (len(blocks), n, d))
+    for j, blk in enumerate(blocks):
+        if hasattr(blk, "before_proj"):
+            w, b = _lin(blk.before_proj, dt, dev)
+            c_new = ops.linear(c_buf, w, b, ops.EPI_BIAS_RES, residual=x, out=ws.get("vace_c2", (n, d)))
+            c_buf = c_new
+        dit_block_forward(blk, c_buf, context, t_mod, rope, ws, ops, exchange)
+        w, b = _lin(blk.after_proj, dt, dev)
+        ops.linear(c_buf, w, b, out=hints[j])
+    return hints
