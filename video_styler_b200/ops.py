@@ -17,6 +17,11 @@ from ._lib import EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_RES, WVD_
 
 Tensor = torch.Tensor
 
+# instrumentation read by bench.py: number of C-ABI kernel launches, and (optionally) CUDA-event pairs around the
+# dominant kernel (self-attention) recorded on the launching stream.
+LAUNCHES = 0
+PROFILE = None      # set to {"self_attention": []} to record (start, end) events
+
 
 def _dt(t: Tensor) -> int:
     if t.dtype == torch.bfloat16:
@@ -52,6 +57,8 @@ def _p(t: Optional[Tensor]):
 
 
 def _stream():
+    global LAUNCHES
+    LAUNCHES += 1
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -164,8 +171,15 @@ def attention(q: Tensor, k: Tensor, v: Tensor, num_heads: int, out: Optional[Ten
     scale = 1.0 / math.sqrt(128.0) if scale is None else scale
     fn = _lib.load().wvd_attention_fwd if q.dtype == torch.bfloat16 else _lib.load().wvd_attention_fwd_f32
     _dt(q)
+    prof = PROFILE is not None and sq == sk
+    if prof:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(fn(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(), _ld(out), num_heads, sq,
              sk, 128, scale, _stream()), "wvd_attention_fwd")
+    if prof:
+        e1.record()
+        PROFILE.setdefault("self_attention", []).append((e0, e1, num_heads, sq))
     return out
 
 
