@@ -222,7 +222,9 @@ def main():
             sampler.start()
         ops.PROFILE = {}
         launches0 = ops.LAUNCHES
+        torch.cuda.nvtx.range_push("wvd_timed")       # ncu --nvtx --nvtx-include "wvd_timed/" isolates the timed region
         ms = timed(step_resident, args.steps)
+        torch.cuda.nvtx.range_pop()
         launches = ops.LAUNCHES - launches0
         prof = ops.PROFILE
         ops.PROFILE = None

@@ -115,11 +115,11 @@ def test_gemm_bf16_all_epilogues(m, n, k):
     for epi in (ops.EPI_BIAS, ops.EPI_BIAS_GELU, ops.EPI_BIAS_RES, ops.EPI_BIAS_GATE_RES):
         out = ops.linear(xd, wd, bd, epi, gd if epi == ops.EPI_BIAS_GATE_RES else None,
                          rd if epi in (ops.EPI_BIAS_RES, ops.EPI_BIAS_GATE_RES) else None)
-        _close(out, _gemm_ref(x, w, b, epi, gate, res), 5e-4, 5e-3)
-    _close(ops.linear(xd, wd), _gemm_ref(x, w, None, 0, None, None), 5e-4, 5e-3)          # no bias
+        _close(out, _gemm_ref(x, w, b, epi, gate, res), 5e-4, 1e-2)       # 1-ulp flips from fp32 summation order
+    _close(ops.linear(xd, wd), _gemm_ref(x, w, None, 0, None, None), 5e-4, 1e-2)          # no bias
     r2 = rd.clone()                                                                      # in-place residual stream
     ops.linear(xd, wd, bd, ops.EPI_BIAS_GATE_RES, gd, r2, out=r2)
-    _close(r2, _gemm_ref(x, w, b, ops.EPI_BIAS_GATE_RES, gate, res), 5e-4, 5e-3)
+    _close(r2, _gemm_ref(x, w, b, ops.EPI_BIAS_GATE_RES, gate, res), 5e-4, 1e-2)
     _no_timeouts()
 
 

@@ -252,7 +252,7 @@ scale_add_kernel(const T* __restrict__ x, const T* __restrict__ y, float scale, 
         IO::load(x + i * VE, a);
         IO::load(y + i * VE, b);
 #pragma unroll
-        for (int e = 0; e < VE; ++e) a[e] = a[e] + IO::rnd(b[e] * scale);   // x + hint * vace_scale
+        for (int e = 0; e < VE; ++e) a[e] = __fadd_rn(a[e], IO::rnd(__fmul_rn(b[e], scale)));   // x + hint * vace_scale (two roundings, no FMA)
         IO::store(out + i * VE, a);
     }
 }
@@ -273,7 +273,7 @@ gate_residual_kernel(const T* __restrict__ x, const T* __restrict__ gate, const 
         IO::load(y + i * VE, b);
         IO::load(gate + c * VE, g);
 #pragma unroll
-        for (int e = 0; e < VE; ++e) a[e] = a[e] + IO::rnd(g[e] * b[e]);
+        for (int e = 0; e < VE; ++e) a[e] = __fadd_rn(a[e], IO::rnd(__fmul_rn(g[e], b[e])));
         IO::store(out + i * VE, a);
     }
 }

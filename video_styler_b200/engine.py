@@ -91,6 +91,20 @@ def _norm_w(m, dtype, device):
     return _param(_unwrap(m).weight, dtype, device)
 
 
+def patch_embed(conv, x: Tensor, ops=_cuda_ops) -> Tensor:
+    """Conv3d with kernel == stride (WanModel.patchify, wan_video_dit.py:339-345; VaceWanModel, wan_video_vace.py:58-59)
+    as im2col + the GEMM kernel: (1, C, F, H, W) -> (F*H'*W', D) tokens in (f, h, w) order.  No cuDNN/TF32 involved."""
+    conv = _unwrap(conv)
+    pt, ph, pw = conv.kernel_size
+    if tuple(conv.stride) != (pt, ph, pw) or x.shape[0] != 1:
+        raise NotImplementedError("patch embedding expects stride == kernel_size and batch 1")
+    _, c, f, h, w = x.shape
+    cols = (x.reshape(c, f // pt, pt, h // ph, ph, w // pw, pw).permute(1, 3, 5, 0, 2, 4, 6)
+            .reshape((f // pt) * (h // ph) * (w // pw), c * pt * ph * pw))
+    wgt = _param(conv.weight, x.dtype, x.device).reshape(conv.weight.shape[0], -1)
+    return ops.linear(cols.contiguous(), wgt, _param(conv.bias, x.dtype, x.device))
+
+
 def block_modulation(block, t_mod: Tensor) -> Tensor:
     """(modulation + t_mod) -> (6, D) rows [shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp]
     (wan_video_dit.py:218-219).  Per-token modulation (4-D t_mod, Wan2.2 TI2V) is not on this path."""
@@ -184,10 +198,7 @@ def vace_forward(vace, x: Tensor, vace_context: Tensor, context: Tensor, t_mod: 
     n, d = x.shape
     if vace_context.shape[0] != 1:
         raise NotImplementedError("batched vace_context: loop over the batch in the caller")
-    pe = _unwrap(vace.vace_patch_embedding)
-    c = torch.nn.functional.conv3d(vace_context.to(dt), _param(pe.weight, dt, dev), _param(pe.bias, dt, dev),
-                                   stride=pe.stride)
-    c = c.flatten(2).transpose(1, 2)[0]                                     # (tokens_total, D)
+    c = patch_embed(vace.vace_patch_embedding, vace_context.to(dt), ops)    # (tokens_total, D)
     if token_slice is not None:
         c = c[token_slice]
     if c.shape[0] > n:

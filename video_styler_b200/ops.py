@@ -82,6 +82,8 @@ def ln_modulate(x: Tensor, shift: Optional[Tensor] = None, scale: Optional[Tenso
     _chk2d(out, "out")
     shift, scale = _vec(shift, d, "shift", x), _vec(scale, d, "scale", x)
     weight, bias = _vec(weight, d, "weight", x), _vec(bias, d, "bias", x)
+    if n == 0:
+        return out
     check(_lib.load().wvd_ln_modulate(x.data_ptr(), _ld(x), _p(shift), _p(scale), _p(weight), _p(bias), out.data_ptr(),
                                       _ld(out), n, d, eps, _dt(x), _stream()), "wvd_ln_modulate")
     return out
@@ -120,6 +122,8 @@ def qk_rmsnorm_rope(q: Tensor, k: Optional[Tensor], wq: Tensor, wk: Optional[Ten
         if frame_ids is not None and (frame_ids.dtype != torch.int32 or not frame_ids.is_cuda):
             raise WvdError("frame_ids must be an int32 CUDA tensor")
     gf, gh, gw = grid
+    if n == 0:
+        return q_out, k_out
     check(_lib.load().wvd_qk_rmsnorm_rope(
         q.data_ptr(), _ld(q), _p(k), _ld(k) if k is not None else 0, wq.data_ptr(), _p(wk), q_out.data_ptr(), _ld(q_out),
         _p(k_out) if k is not None else None, _ld(k_out) if k is not None else 0, n, d, 128, eps, _p(rope_table),
@@ -171,6 +175,10 @@ def attention(q: Tensor, k: Tensor, v: Tensor, num_heads: int, out: Optional[Ten
     scale = 1.0 / math.sqrt(128.0) if scale is None else scale
     fn = _lib.load().wvd_attention_fwd if q.dtype == torch.bfloat16 else _lib.load().wvd_attention_fwd_f32
     _dt(q)
+    if sq == 0:
+        return out
+    if sk == 0:
+        raise WvdError("attention: empty key/value sequence")
     prof = PROFILE is not None and sq == sk
     if prof:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -188,6 +196,8 @@ def scale_add(x: Tensor, y: Tensor, scale: float, out: Optional[Tensor] = None) 
     if not (x.is_cuda and y.is_cuda) or x.shape != y.shape or x.dtype != y.dtype or not x.is_contiguous() or not y.is_contiguous():
         raise WvdError("scale_add: x and y must be contiguous CUDA tensors of equal shape/dtype")
     out = torch.empty_like(x) if out is None else out
+    if x.numel() == 0:
+        return out
     check(_lib.load().wvd_scale_add(x.data_ptr(), y.data_ptr(), float(scale), out.data_ptr(), x.numel(), _dt(x), _stream()),
           "wvd_scale_add")
     return out

@@ -102,9 +102,10 @@ def model_fn_wan_video(
         t_mod = torch.concat([t_mod] * context.shape[0], dim=0)
         t = torch.concat([t] * context.shape[0], dim=0)
 
-    x = dit.patchify(x)                                       # Conv3d k=s=(1,2,2) (:1374)
-    bsz, _, f, h, w = x.shape
-    x = x.flatten(2).transpose(1, 2).contiguous()             # 'b c f h w -> b (f h w) c' (:1381-1382)
+    # patchify: Conv3d k=s=(1,2,2) (:1374) + 'b c f h w -> b (f h w) c' (:1381-1382), as im2col + GEMM
+    pt, ph, pw = engine._unwrap(dit.patch_embedding).kernel_size
+    bsz, f, h, w = x.shape[0], x.shape[2] // pt, x.shape[3] // ph, x.shape[4] // pw
+    x = torch.stack([engine.patch_embed(dit.patch_embedding, x[i:i + 1], ops) for i in range(bsz)], dim=0)
     n_tokens = x.shape[1]
 
     # ---- sequence parallel plan (Ulysses; replaces xfuser USP, wan_video_new.py:1412-1417) ----
