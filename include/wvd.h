@@ -42,6 +42,10 @@ int wvd_sm_arch(void);          /* 100: the only architecture this library is co
 /* Test hook: synchronises the device, copies out and clears the in-kernel watchdog record
  * (out[0] = number of mbarrier waits that timed out, out[1] = tag of the last one, out[2] = block, out[3] = thread). */
 int wvd_debug_flags(unsigned long long out[8]);
+/* Developer hook: when device_buf (>= 128 uint64 of device memory) is non-NULL, subsequent wvd_attention_fwd launches
+ * record per-phase cycle counters of CTA (1,0) into it (softmax warps: wait/ld/max/exp/st; MMA issuer: waits/issue).
+ * Pass NULL to disable (default).                                                                              */
+int wvd_debug_attention_profile(unsigned long long* device_buf);
 
 /* ---- K1/K2: LayerNorm (+ AdaLN modulate) ------------------------------------------------------------
  * out = LN(x) * (1 + scale) + shift            (weight == bias == NULL; shift/scale of length dim)

@@ -16,6 +16,7 @@ SIGNATURES = {
     "wvd_version": [],
     "wvd_sm_arch": [],
     "wvd_debug_flags": [ctypes.POINTER(ctypes.c_ulonglong)],
+    "wvd_debug_attention_profile": [c_void_p],
     "wvd_ln_modulate": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                         c_float, c_int, c_void_p],
     "wvd_qk_rmsnorm_rope": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,

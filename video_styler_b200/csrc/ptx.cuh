@@ -63,6 +63,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         "selp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// non-blocking probe (no hardware suspend): used by pollers that watch several barriers
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// try_wait with an explicit suspend-time hint (ns): the thread sleeps in hardware (no issue slots) until the phase
+// completes or the hint expires
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
 // Bounded wait.  `tag` identifies the call site in the diagnostic record.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag) {
     if (mbar_try_wait(bar, parity)) return;
@@ -244,10 +263,63 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
 }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+
+// ---------------------------------------- packed fp32x2 math (sm_100: FFMA2 / FADD2 / FMUL2) ----------------------------------------
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// 2^x for a pair on the FMA/ALU pipes (no MUFU): x = n + r, n = round(x) via the 1.5*2^23 magic add,
+// 2^r by a degree-3 polynomial on [-0.5, 0.5] (max relative error 7.8e-5, far below the bf16 rounding of P),
+// 2^n by adding n to the exponent field.  Inputs are clamped to >= -125 (masked -inf scores -> 2^-125 ~ 0).
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
+    float x0, x1;
+    f2_unpack(x2, x0, x1);
+    x0 = fmaxf(x0, -125.0f);
+    x1 = fmaxf(x1, -125.0f);
+    const uint64_t xc = f2_pack(x0, x1);
+    const uint64_t t = f2_add(xc, f2_pack(12582912.0f, 12582912.0f));
+    const uint64_t n = f2_add(t, f2_pack(-12582912.0f, -12582912.0f));
+    const uint64_t r = f2_fma(n, f2_pack(-1.0f, -1.0f), xc);
+    uint64_t p = f2_fma(f2_pack(0.05508868396282196f, 0.05508868396282196f), r, f2_pack(0.24260404706001282f, 0.24260404706001282f));
+    p = f2_fma(p, r, f2_pack(0.6932762265205383f, 0.6932762265205383f));
+    p = f2_fma(p, r, f2_pack(0.9999289512634277f, 0.9999289512634277f));
+    float t0, t1, q0, q1;
+    f2_unpack(t, t0, t1);
+    f2_unpack(p, q0, q1);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
 }  // namespace wvd
