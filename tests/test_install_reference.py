@@ -1,0 +1,51 @@
+"""Drop-in check against the REAL reference objects (runs only where /root/reference exists, i.e. in the build
+container): install() on a reference-style pipeline holding the real WanModel / VaceWanModel -- with the real
+GeneralLoRALoader merge and the real enable_vram_management wrappers applied -- must reproduce the reference output.
+The kernels are replaced by the CPU stand-in so this exercises exactly the host-side boundary logic."""
+import types
+
+import pytest
+import torch
+
+from oracle import ref_shim, wan_oracle as O
+from tests import cpu_backend
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="needs /root/reference (build container only)")
+
+
+def test_install_on_real_reference_modules_with_vram_wrappers(golden_dir):
+    import functools
+    import os
+    import video_styler_b200 as V
+    w, dit_mod, vace_mod = ref_shim.load()
+    from diffsynth.lora import GeneralLoRALoader
+    from diffsynth.vram_management import AutoWrappedLinear, AutoWrappedModule, WanAutoCastLayerNorm, enable_vram_management
+    fix = torch.load(os.path.join(golden_dir, "tiny_vace_lora.pt"), weights_only=False)
+    cfg, vcfg = O.DIT_CONFIGS["tiny"], O.VACE_CONFIGS["tiny"]
+    dit = dit_mod.WanModel(has_image_input=False, **cfg)
+    dit.load_state_dict(O.make_state_dict(O.dit_param_shapes(cfg), seed=0, perturb_norms=True), strict=True)
+    vace = vace_mod.VaceWanModel(has_image_input=False, **vcfg)
+    vace.load_state_dict(O.make_state_dict(O.vace_param_shapes(vcfg), seed=3, perturb_norms=True), strict=True)
+    GeneralLoRALoader(device="cpu", torch_dtype=torch.float32).load(vace, O.make_lora_state_dict(vcfg, seed=2, rank=16), alpha=1.0)
+    mcfg = dict(offload_dtype=torch.float32, offload_device="cpu", onload_dtype=torch.float32, onload_device="cpu",
+                computation_dtype=torch.float32, computation_device="cpu")
+    # the module maps of WanVideoPipeline.enable_vram_management (wan_video_new.py:152-184, 272-291)
+    enable_vram_management(dit, module_map={torch.nn.Linear: AutoWrappedLinear, torch.nn.Conv3d: AutoWrappedModule,
+                                            torch.nn.LayerNorm: WanAutoCastLayerNorm, dit_mod.RMSNorm: AutoWrappedModule},
+                           module_config=mcfg)
+    enable_vram_management(vace, module_map={torch.nn.Linear: AutoWrappedLinear, torch.nn.Conv3d: AutoWrappedModule,
+                                             torch.nn.LayerNorm: AutoWrappedModule, dit_mod.RMSNorm: AutoWrappedModule},
+                           module_config=mcfg)
+    assert type(dit.blocks[0].self_attn.q).__name__ == "AutoWrappedLinear"
+    assert type(vace.vace_blocks[0].norm1).__name__ == "AutoWrappedModule"
+    pipe = types.SimpleNamespace(model_fn=w.model_fn_wan_video, dit=dit, vace=vace)
+    V.install(pipe)
+    assert pipe.model_fn is V.model_fn_wan_video
+    inp = O.make_inputs(fix["latent_shape"], cfg["text_dim"], seed=1, with_vace=True)
+    fn = functools.partial(pipe.model_fn, ops=cpu_backend)
+    with torch.no_grad():
+        out = fn(dit=pipe.dit, vace=pipe.vace, latents=inp["latents"], timestep=torch.tensor([fix["timestep"]]),
+                 context=inp["context"], vace_context=inp["vace_context"], vace_scale=1.0,
+                 tea_cache=None, use_unified_sequence_parallel=False, motion_bucket_id=None, cfg_merge=False)
+    m = O.parity_metrics(out, fix["output"])
+    assert m["max_abs"] <= 5e-5 and m["rel_l2"] <= 2e-5, m

@@ -136,7 +136,7 @@ def dit_block_forward(block, x: Tensor, context: Tensor, t_mod: Tensor, rope: Ro
     heads = sa.num_heads
     if getattr(ca, "has_image_input", False):
         raise NotImplementedError("image-conditioned cross attention (k_img/v_img) is not on the wvd path")
-    eps = block.norm1.eps
+    eps = _unwrap(block.norm1).eps
     mod = block_modulation(block, t_mod)
     # ---- self attention: x += gate_msa * o(attn(rope(rms(q)), rope(rms(k)), v)) ----
     h = ops.ln_modulate(x, mod[0], mod[1], eps=eps, out=ws.get("h", (n, d)))
@@ -166,7 +166,7 @@ def dit_block_forward(block, x: Tensor, context: Tensor, t_mod: Tensor, rope: Ro
     w, b = _lin(ca.o, dt, dev)
     ops.linear(a, w, b, ops.EPI_BIAS_RES, residual=x, out=x)
     # ---- ffn: x += gate_mlp * W2 gelu_tanh(W1 modulate(norm2(x))) ----
-    h = ops.ln_modulate(x, mod[3], mod[4], eps=block.norm2.eps, out=ws.get("h", (n, d)))
+    h = ops.ln_modulate(x, mod[3], mod[4], eps=_unwrap(block.norm2).eps, out=ws.get("h", (n, d)))
     w, b = _lin(block.ffn[0], dt, dev)
     mid = ops.linear(h, w, b, ops.EPI_BIAS_GELU, out=ws.get("mid", (n, w.shape[0])))
     w, b = _lin(block.ffn[2], dt, dev)
@@ -181,7 +181,7 @@ def head_forward(head, x: Tensor, t: Tensor, ws: Workspace, ops=_cuda_ops) -> Te
     dt, dev = x.dtype, x.device
     n, d = x.shape
     m = (head.modulation.to(dtype=t.dtype, device=t.device) + t.unsqueeze(1))[0].contiguous()   # (2, D): shift, scale
-    h = ops.ln_modulate(x, m[0], m[1], eps=head.norm.eps, out=ws.get("h", (n, d)))
+    h = ops.ln_modulate(x, m[0], m[1], eps=_unwrap(head.norm).eps, out=ws.get("h", (n, d)))
     w, b = _lin(head.head, dt, dev)
     return ops.linear(h, w, b, out=ws.get("head_out", (n, w.shape[0])))
 
