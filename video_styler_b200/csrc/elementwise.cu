@@ -25,6 +25,16 @@ template <> struct VecIO<__nv_bfloat16> {
         const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
         f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
     }
+    static __device__ __forceinline__ uint4 load_raw(const __nv_bfloat16* p) {
+        uint4 u;   // streaming read: the row is consumed once, keep it out of L1
+        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+        return u;
+    }
+    static __device__ __forceinline__ void unpack(const uint4& u, float* f) {
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+    }
     static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* f) {
         uint4 u;
         u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
@@ -40,11 +50,29 @@ template <> struct VecIO<float> {
         const float4 u = *reinterpret_cast<const float4*>(p);
         f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
     }
+    static __device__ __forceinline__ uint4 load_raw(const float* p) {
+        uint4 u;
+        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+        return u;
+    }
+    static __device__ __forceinline__ void unpack(const uint4& u, float* f) {
+        f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+    }
     static __device__ __forceinline__ void store(float* p, const float* f) {
         *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
     }
     static __device__ __forceinline__ float rnd(float x) { return x; }
 };
+
+// Opaque to the optimiser: stops it from keeping the unpacked fp32 copy of a packed row alive across passes
+// (which would quadruple the live registers and defeat the occupancy the packed layout buys).
+template <int MAXV>
+__device__ __forceinline__ void keep_packed(uint4 (&raw)[MAXV]) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        asm volatile("" : "+r"(raw[i].x), "+r"(raw[i].y), "+r"(raw[i].z), "+r"(raw[i].w));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -57,8 +85,11 @@ constexpr int WARPS_PER_BLOCK = 8;
 // ------------------------------------------------------------------------------------------------
 // LayerNorm + modulate / affine
 // ------------------------------------------------------------------------------------------------
+// The row stays PACKED in registers (16-byte vectors, MAXV per lane) and is unpacked on the fly in each of the three
+// passes (sum, squared deviations, output): 4x fewer live registers than an fp32 copy, so 2 blocks of 8 warps fit per
+// SM and every lane keeps MAXV independent 16-byte loads in flight.
 template <typename T, int MAXV, bool MODULATE, bool AFFINE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (MAXV <= 20 ? 2 : 1))
 ln_modulate_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__ shift, const T* __restrict__ scale,
                    const T* __restrict__ weight, const T* __restrict__ bias, T* __restrict__ out, long long ldo,
                    long long n_tokens, int dim, float eps) {
@@ -69,44 +100,56 @@ ln_modulate_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__
     if (row >= n_tokens) return;
     const int nvec = dim / VE;
     const T* xr = x + row * ldx;
-    float v[MAXV][VE];
-    float sum = 0.f;
+    uint4 raw[MAXV];
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         const int vi = lane + 32 * i;
-        if (vi < nvec) {
-            IO::load(xr + vi * VE, v[i]);
-#pragma unroll
-            for (int e = 0; e < VE; ++e) sum += v[i][e];
-        }
+        if (vi < nvec) raw[i] = IO::load_raw(xr + vi * VE);
     }
-    const float mean = warp_sum(sum) / dim;
-    float sq = 0.f;
+    // One statistics pass: shifted sums around a pivot taken from the row itself (its first element), so that
+    // var = E[(x-p)^2] - (E[x-p])^2 has no cancellation even when |mean| >> std; both reductions share one shuffle tree.
+    float pivot;
+    {
+        float f0[VE];
+        IO::unpack(raw[0], f0);
+        pivot = __shfl_sync(0xffffffffu, f0[0], 0);
+    }
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-        const int vi = lane + 32 * i;
-        if (vi < nvec) {
+        if (lane + 32 * i < nvec) {
+            float f[VE];
+            IO::unpack(raw[i], f);
 #pragma unroll
-            for (int e = 0; e < VE; ++e) { const float d = v[i][e] - mean; sq += d * d; }
+            for (int e = 0; e < VE; ++e) { const float d = f[e] - pivot; s1 += d; s2 = fmaf(d, d, s2); }
         }
     }
-    const float rstd = rsqrtf(warp_sum(sq) / dim + eps);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float dm = s1 / dim;
+    const float mean = pivot + dm;
+    const float rstd = rsqrtf(fmaxf(s2 / dim - dm * dm, 0.f) + eps);
+    keep_packed(raw);
     T* orow = out + row * ldo;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         const int vi = lane + 32 * i;
         if (vi < nvec) {
-            float o[VE];
+            float o[VE], f[VE];
+            IO::unpack(raw[i], f);
             if (AFFINE) {
                 // F.layer_norm(x, weight, bias): ((x - mean) * rstd) * w + b in fp32, one rounding
                 float w[VE], b[VE];
                 IO::load(weight + vi * VE, w);
                 IO::load(bias + vi * VE, b);
 #pragma unroll
-                for (int e = 0; e < VE; ++e) o[e] = (v[i][e] - mean) * rstd * w[e] + b[e];
+                for (int e = 0; e < VE; ++e) o[e] = (f[e] - mean) * rstd * w[e] + b[e];
             } else {
 #pragma unroll
-                for (int e = 0; e < VE; ++e) o[e] = IO::rnd((v[i][e] - mean) * rstd);       // LN output -> dtype
+                for (int e = 0; e < VE; ++e) o[e] = IO::rnd((f[e] - mean) * rstd);       // LN output -> dtype
             }
             if (MODULATE) {
                 // modulate(): x * (1 + scale) + shift evaluated in the tensor dtype (wan_video_dit.py:64-65)
@@ -152,27 +195,34 @@ __device__ __forceinline__ void rms_rope_row(const T* __restrict__ xr, const T* 
     using IO = VecIO<T>;
     constexpr int VE = IO::N;
     const int nvec = dim / VE;
-    float v[MAXV][VE];
+    uint4 raw[MAXV];                     // packed row (see ln_modulate_kernel)
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) raw[i] = IO::load_raw(xr + vi * VE);
+    }
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-        const int vi = lane + 32 * i;
-        if (vi < nvec) {
-            IO::load(xr + vi * VE, v[i]);
+        if (lane + 32 * i < nvec) {
+            float f[VE];
+            IO::unpack(raw[i], f);
 #pragma unroll
-            for (int e = 0; e < VE; ++e) sq += v[i][e] * v[i][e];
+            for (int e = 0; e < VE; ++e) sq += f[e] * f[e];
         }
     }
     const float rstd = rsqrtf(warp_sum(sq) / dim + eps);
+    keep_packed(raw);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         const int vi = lane + 32 * i;
         if (vi < nvec) {
-            float ww[VE], o[VE];
+            float ww[VE], o[VE], f[VE];
+            IO::unpack(raw[i], f);
             IO::load(w + vi * VE, ww);
 #pragma unroll
             for (int e = 0; e < VE; ++e)   // norm(x.float()).to(dtype) * weight  (wan_video_dit.py:109-111)
-                o[e] = IO::rnd(IO::rnd(v[i][e] * rstd) * ww[e]);
+                o[e] = IO::rnd(IO::rnd(f[e] * rstd) * ww[e]);
             if (ROPE) {
 #pragma unroll
                 for (int pr = 0; pr < VE / 2; ++pr) {   // (re, im) * (cos + i sin)  (wan_video_dit.py:92-97)
@@ -186,8 +236,9 @@ __device__ __forceinline__ void rms_rope_row(const T* __restrict__ xr, const T* 
     }
 }
 
+// blockIdx.y selects the tensor (0 = q, 1 = k): q and k rows are independent, one warp each.
 template <typename T, int MAXV, bool ROPE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (MAXV <= 20 ? 2 : 1))
 qk_rmsnorm_rope_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ k, long long ldk,
                        const T* __restrict__ wq, const T* __restrict__ wk, T* __restrict__ qo, long long ldqo,
                        T* __restrict__ ko, long long ldko, long long n_tokens, int dim, float eps,
@@ -216,15 +267,15 @@ qk_rmsnorm_rope_kernel(const T* __restrict__ q, long long ldq, const T* __restri
             cs[pr] = __ldg(rope_cs + (static_cast<long long>(axis) * 1024 + pos) * 32 + jj);
         }
     }
-    rms_rope_row<T, MAXV, ROPE>(q + row * ldq, wq, qo + row * ldqo, dim, eps, lane, cs);
-    if (k != nullptr) rms_rope_row<T, MAXV, ROPE>(k + row * ldk, wk, ko + row * ldko, dim, eps, lane, cs);
+    if (blockIdx.y == 0) rms_rope_row<T, MAXV, ROPE>(q + row * ldq, wq, qo + row * ldqo, dim, eps, lane, cs);
+    else rms_rope_row<T, MAXV, ROPE>(k + row * ldk, wk, ko + row * ldko, dim, eps, lane, cs);
 }
 
 template <typename T, int MAXV>
 int launch_rms(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* wq, const void* wk, void* qo,
                int64_t ldqo, void* ko, int64_t ldko, int64_t n, int dim, float eps, const void* rope_cs,
                const int32_t* frame_ids, int gh, int gw, int64_t token_offset, cudaStream_t s) {
-    const unsigned grid = static_cast<unsigned>((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    const dim3 grid(static_cast<unsigned>((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), k != nullptr ? 2 : 1);
     const dim3 block(WARPS_PER_BLOCK * 32);
     if (rope_cs != nullptr)
         qk_rmsnorm_rope_kernel<T, MAXV, true><<<grid, block, 0, s>>>(
