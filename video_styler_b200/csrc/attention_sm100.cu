@@ -3,25 +3,31 @@
 //   out[s, h] = softmax(q_h k_h^T * scale) v_h          non-causal, no mask, no dropout
 //   (replaces flash_attention(), diffsynth/models/wan_video_dit.py:28-61; self: Sk = Sq ~ 30k-76k, cross: Sk = 512)
 //
-// One CTA = one head x 256 query rows (two 128-row Q tiles, ping-pong), 384 threads:
-//   warps 0-3 / 4-7     softmax warpgroup for Q tile 0 / 1: one query row per thread; S row TMEM->registers,
-//                       running max with lazy rescale (only when the max grows by > 2^8), exp2 (MUFU, packed fp32x2
-//                       scale/sum), P (bf16) written back to TMEM over the S columns, row sum in fp32; final O / l -> global
-//   warp 8 (1 thread)   TMA producer: Q tiles once, then K_j, V_j (128x128 bf16, 128-byte swizzle) through a 4-slot ring
-//   warp 9 (1 thread)   MMA issuer  : S_i = Q_i K_j^T   (SS, K-major A and B, 128x128x16 x8) -> TMEM
+// One CTA = one head x 256 query rows (two 128-row Q tiles, ping-pong), 576 threads:
+//   warps 0-7 / 8-15    softmax warps of Q tile 0 / 1.  TWO threads per query row (warps w and w+4 of a tile share a
+//                       TMEM lane quarter and a scheduler): each owns 64 of the 128 score columns of its row.  A lone
+//                       warp cannot keep the MUFU pipe busy (in-order issue exposes the MUFU latency: ~70 % of the
+//                       16 exp2/clk/SM); two warps per scheduler can, so a tile's exponentials run at the full rate
+//                       and the two tiles TAKE TURNS on the pipe (named barriers) -- one tile's exponentials overlap the
+//                       other tile's PV / QK^T on the tensor core.
+//                       exp2 runs against a STALE reference maximum: the row maximum of the tile is computed in the
+//                       issue slots the MUFU stream leaves free, exchanged between the two threads of the row through
+//                       shared memory, and only guards against overflow (the reference moves when exceeded by 2^8).
+//                       P (bf16) goes back to TMEM over the S columns in two hand-overs of 64 keys so that PV of the
+//                       first overlaps the exponentials of the second; row sums in fp32; final O / l -> global.
+//   warp 16 (1 thread)  TMA producer: Q tiles once, then K_j, V_j (128x128 bf16, 128-byte swizzle) through a 4-slot ring
+//   warp 17 (1 thread)  MMA issuer  : S_i = Q_i K_j^T   (SS, K-major A and B, 128x128x16 x8) -> TMEM
 //                                     O_i += P_i V_j    (TS: P from TMEM, V MN-major from smem, 128x128x16 x8) -> TMEM
-//   warp 10             TMEM allocator (512 columns)
-// While warpgroup i does softmax on S_i(j), the tensor core runs PV / QK^T of the other tile.
+//                       (the whole warp allocates / frees the 512 TMEM columns)
 // TMEM map (512 columns): S0 [0,128) | S1 [128,256) | O0 [256,384) | O1 [384,512); P_i aliases S_i[0,64).
 // KV tail (Sk % 128 != 0): TMA zero-fills, the softmax masks the tail columns to -inf.  Q tail rows are not stored.
-// Measured structure of one KV step (ncu + in-kernel cycle counters, profiles/): tensor pipe 2048 cycles nominal,
-// MUFU.EX2 2048 cycles (16/clk/SM) -- the two pipes are co-critical and coupled through the S->P->S dependency
-// chain of each tile, which is what bounds the kernel at ~56 % tensor-pipe activity.
+// Budget of one KV step per SM: tensor pipe 2048 cycles (4 x 128x128x128), MUFU.EX2 2048 cycles (256 x 128 / 16 per clk).
 #include <math.h>
 #include <stdlib.h>
 
 #include "host_utils.h"
 #include "ptx.cuh"
+#include "softmax_math.cuh"
 
 namespace wvd {
 namespace attn {
@@ -30,29 +36,41 @@ constexpr int BQ = 128;               // rows per Q tile
 constexpr int QT = 2;                 // Q tiles per CTA
 constexpr int BKV = 128;              // keys per KV tile
 constexpr int HD = 128;               // head dim
+constexpr int NS = BKV / 2;           // score columns per softmax thread
 constexpr int TILE_BYTES = 128 * 128 * 2;     // 32 KB
 constexpr int HALF_BYTES = TILE_BYTES / 2;    // one 64-column TMA box
 constexpr int SLOTS = 4;              // K/V ring slots
-constexpr int NUM_THREADS = 384;
-constexpr int SMEM_BYTES = QT * TILE_BYTES + SLOTS * TILE_BYTES + 1024 + 256;
+// Warp roles.  The control warps get the HIGHEST warp ids: the SM's issue arbiter favours higher warp ids, and the
+// single MMA-issuing thread must never wait behind the softmax warps for an issue slot.
+constexpr int SOFTMAX_WARPS = 16;
+constexpr int TMA_WARP = 16, MMA_WARP = 17, ALLOC_WARP = 17;     // the MMA warp also owns the TMEM allocation
+constexpr int NUM_THREADS = 18 * 32;
+// Registers: 576 threads x 112 = 64,512 of the SM's 65,536 (the allocation unit is 16 per thread; a 19th warp would
+// cap every thread at 96).  setmaxnreg.inc can only take registers that other warps of the CTA have released, and two
+// control warps cannot release enough to matter for 512 softmax threads, so the softmax code is written to fit the
+// launch allocation (64 score columns + 32 packed P columns per thread).
+constexpr int BAR_BYTES = 256;
+constexpr int XCHG_BYTES = 2 * QT * 2 * BQ * 4;          // [step parity][tile][half][row] fp32
+constexpr int SMEM_BYTES = QT * TILE_BYTES + SLOTS * TILE_BYTES + BAR_BYTES + XCHG_BYTES + 1024;
 constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);   // A = Q (K-major), B = K (K-major)
 constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 128, 0, 1);   // A = P (TMEM), B = V (MN-major)
-constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
-// Warp roles.  The control warps get the HIGHEST warp ids: the SM's issue arbiter favours higher warp ids, and the
-// single MMA-issuing thread must never wait behind the eight softmax warps for an issue slot.
-#ifndef WVD_ATTN_NCHUNK
-#define WVD_ATTN_NCHUNK 1
+#ifndef WVD_ATTN_HO0_GROUPS
+#define WVD_ATTN_HO0_GROUPS 3
 #endif
-constexpr int NCHUNK = WVD_ATTN_NCHUNK;     // P is produced / consumed in NCHUNK chunks of 128/NCHUNK keys (1, 2 or 4)
-constexpr int CTRL_WARP0 = 8, TMA_WARP = 8, MMA_WARP = 9, ALLOC_WARP = 10;
+#ifndef WVD_ATTN_RELEASE_GROUP
+#define WVD_ATTN_RELEASE_GROUP 3
+#endif
+constexpr int GC = 16;                                  // columns per exp2 / store group (4 groups per thread)
+constexpr int HO0_GROUPS = WVD_ATTN_HO0_GROUPS;         // groups in the first hand-over of P (the rest form the second)
+constexpr int RELEASE_GROUP = WVD_ATTN_RELEASE_GROUP;   // the other tile's turn starts once this group's exponentials are issued
+constexpr float REF_MARGIN = 8.0f;    // log2 units: the softmax reference point moves when the row maximum exceeds it by 2^8
 
 struct Params {
     __nv_bfloat16* out;
     long long ldo;
     int sq, sk, n_kv;
     float scale_log2;
-    unsigned long long* prof;   // optional device buffer (developer profiling, see wvd_debug_attention_profile)
-    int dbg;                    // developer timing experiments (WVD_ATTN_DEBUG): 1 = skip softmax math, 2 = skip QK MMAs, 4 = skip PV MMAs
+    unsigned long long* prof;   // optional device buffer (developer profiling, -DWVD_ATTN_PROF builds only)
 };
 
 __device__ __forceinline__ uint32_t clk32() {
@@ -60,10 +78,12 @@ __device__ __forceinline__ uint32_t clk32() {
     asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
     return c;
 }
+#ifdef WVD_ATTN_PROF
+#define PROF_LAP(acc) do { if (prof) { const uint32_t t_ = clk32(); (acc) += t_ - pt; pt = t_; } } while (0)
+#else
+#define PROF_LAP(acc) do { } while (0)
+#endif
 
-// EMU_OF_4: how many of every 4 consecutive column pairs take exp2 on the FMA pipes (polynomial) instead of MUFU.
-// MUFU.EX2 runs at 16/clk/SM: 256 rows x 128 columns per KV step = 2048 cycles, exactly the tensor-pipe time of the
-// step; moving part of the exponentials to the FMA pipes takes the XU pipe off the critical path.
 template <int EMU_OF_4>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -80,8 +100,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     auto kv_empty = [&](int s) { return bar_base + 40 + s * 8; };
     auto s_full = [&](int i) { return bar_base + 72 + i * 8; };
     auto o_full = [&](int i) { return bar_base + 88 + i * 8; };
-    auto p_full = [&](int i, int c) { return bar_base + 104 + (i * NCHUNK + c) * 8; };   // P chunk c of tile i is in TMEM
+    auto p_full = [&](int i, int c) { return bar_base + 104 + (i * 2 + c) * 8; };   // hand-over c of tile i is in TMEM
+    const uint32_t turn_word = bar_base + 160;                                      // always zero (see the softmax loop)
     const uint32_t tmem_slot = bar_base + 176;
+    const uint32_t xchg = bar_base + BAR_BYTES;
     volatile uint32_t* tmem_slot_gen =
         reinterpret_cast<volatile uint32_t*>(smem_gen + (QT + SLOTS) * TILE_BYTES + 176);
 
@@ -98,13 +120,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     if (warp == MMA_WARP && lane == 0) {
         mbar_init(q_full, 1);
+        st_shared_u32(turn_word, 0u);
         for (int s = 0; s < SLOTS; ++s) {
             mbar_init(kv_full(s), 1);
             mbar_init(kv_empty(s), 1);
         }
         for (int i = 0; i < QT; ++i) {
             mbar_init(s_full(i), 1);
-            for (int c = 0; c < NCHUNK; ++c) mbar_init(p_full(i, c), 4);      // one arrival per softmax warp
+            for (int c = 0; c < 2; ++c) mbar_init(p_full(i, c), SOFTMAX_WARPS / QT);      // one arrival per softmax warp
             mbar_init(o_full(i), 1);
         }
         fence_barrier_init();
@@ -118,9 +141,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
-    if (warp >= CTRL_WARP0) {
-        setmaxnreg_dec<72>();
-        if (warp == TMA_WARP && lane == 0) {
+    if (warp >= SOFTMAX_WARPS) {
+        if (warp == TMA_WARP && elect_one()) {
             // ------------------------------ TMA producer ------------------------------
             mbar_expect_tx(q_full, QT * TILE_BYTES);
 #pragma unroll
@@ -128,6 +150,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tma_load_2d(q_smem + i * TILE_BYTES, &tmQ, q_full, head * HD, q_row0 + i * BQ);
                 tma_load_2d(q_smem + i * TILE_BYTES + HALF_BYTES, &tmQ, q_full, head * HD + 64, q_row0 + i * BQ);
             }
+#pragma unroll 1
             for (int t = 0; t < 2 * n_kv; ++t) {
                 const int slot = t % SLOTS;
                 const uint32_t ph = (t / SLOTS) & 1;
@@ -139,12 +162,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tma_load_2d(dst, tm, kv_full(slot), head * HD, j * BKV);
                 tma_load_2d(dst + HALF_BYTES, tm, kv_full(slot), head * HD + 64, j * BKV);
             }
-        } else if (warp == MMA_WARP && lane == 0) {
+        } else if (warp == MMA_WARP && elect_one()) {
             // ------------------------------ MMA issuer ------------------------------
             // Every mbarrier probe costs ~100 cycles of latency on this single thread, so the schedule is a fixed
-            // ping-pong with as few waits as possible (an event-driven poller over both tiles measured 2x slower).
+            // ping-pong (an event-driven poller over both tiles measured 2x slower); the K/V waits sit at the top of
+            // the step, off the P -> PV -> QK chain of either tile.
             auto issue_qk = [&](int i, uint32_t k_addr) {
-                if (p.dbg & 2) return;
                 const uint32_t qa = q_smem + i * TILE_BYTES;
                 const uint32_t d = tmem_base + i * 128;
 #pragma unroll
@@ -154,19 +177,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                             IDESC_QK, kk != 0 ? 1u : 0u);
                 }
             };
-            auto issue_pv = [&](int i, uint32_t v_addr, bool accumulate, uint32_t pph) {
+            // O_i += P_i[:, keys of hand-over c] V[keys of hand-over c, :].  Group g of half h of the tile holds keys
+            // [64h + 16g, 64h + 16g + 16), i.e. the 16-key MMA step kk = 4h + g; hand-over 0 = groups [0, HO0_GROUPS).
+            auto issue_pv = [&](int i, uint32_t v_addr, bool accumulate, int c) {
                 const uint32_t d = tmem_base + 256 + i * 128;
                 const uint32_t pa = tmem_base + i * 128;
+                const int g0 = c == 0 ? 0 : HO0_GROUPS, g1 = c == 0 ? HO0_GROUPS : NS / GC;
+                bool first = !accumulate;
 #pragma unroll
-                for (int c = 0; c < NCHUNK; ++c) {
-                    mbar_wait(p_full(i, c), pph, 0x230 + i * 8 + c);
-                    tc_fence_after();
-                    if (p.dbg & 4) continue;
+                for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-                    for (int kk = c * (8 / NCHUNK); kk < (c + 1) * (8 / NCHUNK); ++kk) {
+                    for (int g = 0; g < NS / GC; ++g) {
+                        if (g < g0 || g >= g1) continue;
+                        const int kk = 4 * hh + g;
                         // V tile: kv rows of 128 B (64 d-columns) per box; 16 kv rows = 2048 B; second d-half at +16 KB
                         umma_ts(d, pa + kk * 8, make_smem_desc_sw128(v_addr + kk * 2048, HALF_BYTES, 1024), IDESC_PV,
-                                (accumulate || kk != 0) ? 1u : 0u);
+                                first ? 0u : 1u);
+                        first = false;
                     }
                 }
             };
@@ -181,162 +208,176 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             issue_qk(1, kv_smem + slot_of(0) * TILE_BYTES);
             tc_commit(s_full(1));
             tc_commit(kv_empty(slot_of(0)));
+#pragma unroll 1
             for (int j = 0; j < n_kv; ++j) {
                 const int tv = 2 * j + 1, tk = 2 * j + 2;
                 const uint32_t pph = j & 1;
                 const bool more = j + 1 < n_kv;
                 mbar_wait(kv_full(slot_of(tv)), phase_of(tv), 0x220);
+                if (more) mbar_wait(kv_full(slot_of(tk)), phase_of(tk), 0x240);
                 const uint32_t v_addr = kv_smem + slot_of(tv) * TILE_BYTES;
                 const uint32_t k_addr = kv_smem + slot_of(tk) * TILE_BYTES;
-                // tile 0
-                issue_pv(0, v_addr, j > 0, pph);
-                if (more) {
-                    mbar_wait(kv_full(slot_of(tk)), phase_of(tk), 0x240);
+#pragma unroll
+                for (int i = 0; i < QT; ++i) {
+                    mbar_wait(p_full(i, 0), pph, 0x230 + i * 8);
                     tc_fence_after();
-                    issue_qk(0, k_addr);
-                    tc_commit(s_full(0));
-                } else {
-                    tc_commit(o_full(0));
-                }
-                // tile 1
-                issue_pv(1, v_addr, j > 0, pph);
-                tc_commit(kv_empty(slot_of(tv)));
-                if (more) {
-                    issue_qk(1, k_addr);
-                    tc_commit(s_full(1));
-                    tc_commit(kv_empty(slot_of(tk)));
-                } else {
-                    tc_commit(o_full(1));
+                    issue_pv(i, v_addr, j > 0, 0);
+                    mbar_wait(p_full(i, 1), pph, 0x231 + i * 8);
+                    tc_fence_after();
+                    issue_pv(i, v_addr, true, 1);
+                    if (i == QT - 1) tc_commit(kv_empty(slot_of(tv)));
+                    if (more) {
+                        issue_qk(i, k_addr);
+                        tc_commit(s_full(i));
+                        if (i == QT - 1) tc_commit(kv_empty(slot_of(tk)));
+                    } else {
+                        tc_commit(o_full(i));
+                    }
                 }
             }
         }
     } else {
-        // ------------------------------ softmax warpgroups ------------------------------
-        setmaxnreg_inc<216>();
-        const int i = warp >> 2;                    // Q tile of this warpgroup (warps 0-3 / 4-7)
+        // ------------------------------ softmax warps ------------------------------
+        const int i = warp >> 3;                    // Q tile of this warp (warps 0-7 / 8-15)
+        const int h = (warp >> 2) & 1;              // which 64 score columns of the row this thread owns
         const int quarter = warp & 3;               // TMEM lane quarter accessible to this warp
+        const int r = quarter * 32 + lane;          // row within the tile
         const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
-        const uint32_t s_tmem = tmem_base + i * 128 + lane_sel;
+        const uint32_t s_tmem = tmem_base + i * 128 + lane_sel + h * NS;            // my score columns
+        const uint32_t p_tmem = tmem_base + i * 128 + lane_sel + h * (NS / 2);      // my P columns (bf16 pairs)
         const uint32_t o_tmem = tmem_base + 256 + i * 128 + lane_sel;
-        const int row = q_row0 + i * BQ + quarter * 32 + lane;
+        const int row = q_row0 + i * BQ + r;
         const float sl2 = p.scale_log2;
-        const int tail_valid = p.sk - (n_kv - 1) * BKV;     // valid keys in the last KV tile (1..128)
-        float m = -INFINITY;   // running max of the raw scores (reference point of the stored exponentials)
-        float l = 0.f;
+        const uint64_t sl2_2 = f2_pack(sl2, sl2);
+        const int tail_valid = p.sk - (n_kv - 1) * BKV - h * NS;    // my valid columns in the last KV tile (may be <= 0)
+        const uint32_t pair_bar = 3 + i * 4 + quarter;              // named barrier of the two warps that share my rows
+        auto xchg_mine = [&](int par) { return xchg + (((par * QT + i) * 2 + h) * BQ + r) * 4; };
+        auto xchg_other = [&](int par) { return xchg + (((par * QT + i) * 2 + (1 - h)) * BQ + r) * 4; };
+        // Reference point of the stored exponentials (raw-score units), identical in the two threads of a row.  It is
+        // the true row maximum of the first KV tile and moves only when a later tile's row maximum exceeds it by more
+        // than REF_MARGIN (softmax is invariant to the reference; fp32 and bf16 share the exponent range, so a stale
+        // reference costs no precision until it would overflow).
+        float m = -INFINITY;
+        float l = 0.f;                              // sum over MY columns
 
+        if (i == 1) named_bar_arrive(1, 2 * (BQ * 2));      // tile 0 takes the first turn
+#ifdef WVD_ATTN_PROF
         const bool prof = p.prof != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && lane == 0;
-        uint32_t pc_wait = 0, pc_ld = 0, pc_max = 0, pc_exp = 0, pc_st = 0, pt = 0;
+        uint32_t pc_wait = 0, pc_ld = 0, pc_turn = 0, pc_max = 0, pc_b = 0, pc_redo = 0, pc_x1 = 0, pc_x2 = 0, pt = 0;
+#endif
+#pragma unroll 1
         for (int j = 0; j < n_kv; ++j) {
+#ifdef WVD_ATTN_PROF
             if (prof) pt = clk32();
+#endif
             mbar_wait(s_full(i), j & 1, 0x300 + i);
             tc_fence_after();
-            if (prof) { const uint32_t t = clk32(); pc_wait += t - pt; pt = t; }
-            if (p.dbg & 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) { for (int c = 0; c < NCHUNK; ++c) mbar_arrive(p_full(i, c)); }
-                continue;
-            }
-            uint32_t s[128];
+            PROF_LAP(pc_wait);
+            uint32_t s[NS];
             tmem_ld_32x32b_x32(s_tmem + 0, s + 0);
             tmem_ld_32x32b_x32(s_tmem + 32, s + 32);
-            tmem_ld_32x32b_x32(s_tmem + 64, s + 64);
-            tmem_ld_32x32b_x32(s_tmem + 96, s + 96);
             tc_wait_ld();
-            if (prof) { const uint32_t t = clk32(); pc_ld += t - pt; pt = t; }
-            if (j == n_kv - 1 && tail_valid < BKV) {
+            PROF_LAP(pc_ld);
+            if (j == n_kv - 1 && tail_valid < NS) {
 #pragma unroll
-                for (int c = 0; c < 128; ++c)
+                for (int c = 0; c < NS; ++c)
                     if (c >= tail_valid) s[c] = 0xff800000u;   // -inf
             }
-            float mx[8];
-#pragma unroll
-            for (int a = 0; a < 8; ++a) mx[a] = fmaxf(__uint_as_float(s[2 * a]), __uint_as_float(s[2 * a + 1]));
-#pragma unroll
-            for (int c = 16; c < 128; c += 16) {
-#pragma unroll
-                for (int a = 0; a < 8; ++a) mx[a] = fmax3(mx[a], __uint_as_float(s[c + 2 * a]), __uint_as_float(s[c + 2 * a + 1]));
-            }
-            const float m_new = fmaxf(fmax3(fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])), m);
-            if (j == 0) {
-                m = m_new;
-            } else {
-                const bool grow = (m_new - m) * sl2 > RESCALE_THRESHOLD;
-                if (__any_sync(0xffffffffu, grow)) {
-                    // O_i(j-1) is complete (s_full(j) was committed after PV_i(j-1)); rescale this row
-                    const float alpha = fast_exp2((m - m_new) * sl2);
+            // Row maximum of the tile -- only a guard against overflow of the stale reference.  Each thread reduces its
+            // 64 columns; the two threads of a row exchange through shared memory (double-buffered by step parity).
+            // All of this sits BEFORE the tile's turn on the MUFU pipe, i.e. normally in the shadow of the other
+            // tile's exponentials.  The pair barrier also orders the P stores below after BOTH threads' S loads.
+            const float mine = row_max<NS, 0, NS>(s, m);
+#ifdef WVD_ATTN_PROF
+            if (prof) { const uint32_t t = clk32() + (__float_as_uint(mine) & 0u); pc_x1 += t - pt; pt = t; }
+#endif
+            st_shared_u32(xchg_mine(j & 1), __float_as_uint(mine));
+            named_bar_sync(pair_bar, 64);
+            const float mx = fmaxf(mine, __uint_as_float(ld_shared_volatile_u32(xchg_other(j & 1))));
+#ifdef WVD_ATTN_PROF
+            if (prof) { const uint32_t t = clk32() + (__float_as_uint(mx) & 0u); pc_x2 += t - pt; pt = t; }
+#endif
+            // first tile: m = -inf and the comparison is true.  Warp-uniform, identical in the two warps of the pair.
+            if (__any_sync(0xffffffffu, (mx - m) * sl2 > REF_MARGIN)) {
+                // Move the reference to mx.  Every PV of the previous steps has completed (s_full(j) was committed
+                // after them); the h = 0 thread of the row rescales its O accumulator, and the tensor core cannot
+                // touch O again before all eight warps of the tile have handed P over.
+                if (j > 0) {
+                    const float alpha = fast_exp2((m - mx) * sl2);
                     l *= alpha;
-                    m = m_new;
+                    if (h == 0) {
 #pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t o[32];
-                        tmem_ld_32x32b_x32(o_tmem + c * 32, o);
-                        tc_wait_ld();
+                        for (int c = 0; c < 8; ++c) {
+                            uint32_t o[16];
+                            tmem_ld_32x32b_x16(o_tmem + c * 16, o);
+                            tc_wait_ld();
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-                        tmem_st_32x32b_x32(o_tmem + c * 32, o);
+                            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                            tmem_st_32x32b_x16(o_tmem + c * 16, o);
+                        }
+                        tc_wait_st();
                     }
+                }
+                m = mx;
+#ifdef WVD_ATTN_PROF
+                if (prof) ++pc_redo;
+#endif
+            }
+            PROF_LAP(pc_max);
+            // My tile's turn on the MUFU pipe.  BAR.SYNC is deferred-blocking: the warp only stops at the next
+            // instruction that depends on barrier-protected memory, so the exponentials are made to depend on a
+            // (zero) word read after it.
+            named_bar_sync(1 + i, 2 * (BQ * 2));
+            const float turn_zero = __uint_as_float(ld_shared_volatile_u32(turn_word));
+#ifdef WVD_ATTN_PROF
+            if (prof) { const uint32_t t = clk32() + __float_as_uint(turn_zero); pc_turn += t - pt; pt = t; }
+#endif
+            // Exponentials in groups of GC columns, each group stored to TMEM as soon as it is packed (few live
+            // registers).
+            const float neg_m = -m * sl2 + turn_zero;
+            const uint64_t negm_2 = f2_pack(neg_m, neg_m);
+            float lsum = 0.f;
+#pragma unroll
+            for (int g = 0; g < NS / GC; ++g) {
+                uint32_t pk[GC / 2];
+                switch (g) {   // compile-time after unrolling
+                    case 0: lsum += exp_chunk<NS, 0 * GC, 1 * GC, EMU_OF_4>(s, pk, sl2_2, negm_2); break;
+                    case 1: lsum += exp_chunk<NS, 1 * GC, 2 * GC, EMU_OF_4>(s, pk, sl2_2, negm_2); break;
+                    case 2: lsum += exp_chunk<NS, 2 * GC, 3 * GC, EMU_OF_4>(s, pk, sl2_2, negm_2); break;
+                    default: lsum += exp_chunk<NS, 3 * GC, 4 * GC, EMU_OF_4>(s, pk, sl2_2, negm_2); break;
+                }
+                if (g == RELEASE_GROUP && (i == 0 || j + 1 < n_kv)) named_bar_arrive(2 - i, 2 * (BQ * 2));   // the other tile's turn
+                store_p<GC / 2>(p_tmem + g * (GC / 2), pk);
+                if (g == HO0_GROUPS - 1 || g == NS / GC - 1) {
+                    // hand-over; the other warp of my scheduler keeps the MUFU pipe busy meanwhile
                     tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(p_full(i, g == NS / GC - 1 ? 1 : 0));
                 }
             }
-            if (prof) { const uint32_t t = clk32(); pc_max += t - pt; pt = t; }
-            const float neg_m = -m * sl2;
-            const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
-            uint64_t lsum_a = f2_pack(0.f, 0.f), lsum_b = f2_pack(0.f, 0.f);
-#pragma unroll
-            for (int ch = 0; ch < NCHUNK; ++ch) {
-                constexpr int CW = BKV / NCHUNK;          // keys per chunk
-                uint32_t pk[CW / 2];
-#pragma unroll
-                for (int cc = 0; cc < CW; cc += 2) {
-                    const int c = ch * CW + cc;
-                    const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), sl2_2, negm_2);
-                    float p0, p1;
-                    if (((c >> 1) & 3) < EMU_OF_4) {
-                        exp2_poly2(x2, p0, p1);
-                    } else {
-                        float x0, x1;
-                        f2_unpack(x2, x0, x1);
-                        p0 = fast_exp2(x0);
-                        p1 = fast_exp2(x1);
-                    }
-                    if (c & 2) lsum_b = f2_add(lsum_b, f2_pack(p0, p1));
-                    else lsum_a = f2_add(lsum_a, f2_pack(p0, p1));
-                    pk[cc >> 1] = pack_bf16x2(p0, p1);
-                }
-                if (CW == 32) {
-                    tmem_st_32x32b_x16(s_tmem + ch * 16, pk);
-                } else {
-#pragma unroll
-                    for (int q4 = 0; q4 < CW / 64; ++q4) tmem_st_32x32b_x32(s_tmem + ch * (CW / 2) + q4 * 32, pk + q4 * 32);
-                }
-                tc_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(p_full(i, ch));
-            }
-            {
-                float a0, a1;
-                f2_unpack(f2_add(lsum_a, lsum_b), a0, a1);
-                l += a0 + a1;
-            }
-            if (prof) { const uint32_t t = clk32(); pc_exp += t - pt; pt = t; }
-            if (prof) { const uint32_t t = clk32(); pc_st += t - pt; pt = t; }
+            l += lsum;
+            PROF_LAP(pc_b);
         }
+#ifdef WVD_ATTN_PROF
         if (prof) {
             unsigned long long* o = p.prof + warp * 8;
-            o[0] = pc_wait; o[1] = pc_ld; o[2] = pc_max; o[3] = pc_exp; o[4] = pc_st; o[5] = n_kv;
+            o[0] = pc_wait; o[1] = pc_ld; o[2] = pc_max; o[3] = pc_b; o[4] = pc_redo; o[5] = n_kv; o[6] = pc_turn; o[7] = (static_cast<unsigned long long>(pc_x1) << 32) | pc_x2;
         }
+#endif
 
         // ------------------------------ epilogue: O / l -> global ------------------------------
+        // row sum = my columns + the other thread's
+        st_shared_u32(xchg_mine(0), __float_as_uint(l));
+        named_bar_sync(pair_bar, 64);
+        const float inv_l = 1.0f / (l + __uint_as_float(ld_shared_volatile_u32(xchg_other(0))));
         mbar_wait(o_full(i), 0, 0x310 + i);
         tc_fence_after();
-        const float inv_l = 1.0f / l;
-        __nv_bfloat16* orow = p.out + static_cast<long long>(row) * p.ldo + head * HD;
+        __nv_bfloat16* orow = p.out + static_cast<long long>(row) * p.ldo + head * HD + h * (HD / 2);
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
-            tmem_ld_32x32b_x32(o_tmem + c * 32, o);
+            tmem_ld_32x32b_x32(o_tmem + h * (HD / 2) + c * 32, o);
             tc_wait_ld();
             if (row < p.sq) {
 #pragma unroll
@@ -402,11 +443,6 @@ extern "C" __attribute__((visibility("default"))) int wvd_attention_fwd(const vo
     p.n_kv = (int)((sk + attn::BKV - 1) / attn::BKV);
     p.scale_log2 = scale * 1.4426950408889634f;
     p.prof = attn::g_prof_buffer;
-    {
-        static int dbg = -1;
-        if (dbg < 0) { const char* e = getenv("WVD_ATTN_DEBUG"); dbg = e ? atoi(e) : 0; }
-        p.dbg = dbg;
-    }
     static int emu = -1;
     if (emu < 0) {
         const char* e = getenv("WVD_ATTN_EMU");        // tuning knob: 0..3 of every 4 column pairs on the FMA pipes

@@ -106,32 +106,31 @@ ln_modulate_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__
         const int vi = lane + 32 * i;
         if (vi < nvec) raw[i] = IO::load_raw(xr + vi * VE);
     }
-    // One statistics pass: shifted sums around a pivot taken from the row itself (its first element), so that
-    // var = E[(x-p)^2] - (E[x-p])^2 has no cancellation even when |mean| >> std; both reductions share one shuffle tree.
-    float pivot;
-    {
-        float f0[VE];
-        IO::unpack(raw[0], f0);
-        pivot = __shfl_sync(0xffffffffu, f0[0], 0);
-    }
-    float s1 = 0.f, s2 = 0.f;
+    // Two statistics passes over the packed registers (mean, then squared deviations about the mean): the same
+    // cancellation-free fp32 arithmetic as F.layer_norm; unpacking twice is cheaper than keeping an fp32 copy live.
+    float s1 = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         if (lane + 32 * i < nvec) {
             float f[VE];
             IO::unpack(raw[i], f);
 #pragma unroll
-            for (int e = 0; e < VE; ++e) { const float d = f[e] - pivot; s1 += d; s2 = fmaf(d, d, s2); }
+            for (int e = 0; e < VE; ++e) s1 += f[e];
         }
     }
+    const float mean = warp_sum(s1) / dim;
+    keep_packed(raw);
+    float s2 = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    for (int i = 0; i < MAXV; ++i) {
+        if (lane + 32 * i < nvec) {
+            float f[VE];
+            IO::unpack(raw[i], f);
+#pragma unroll
+            for (int e = 0; e < VE; ++e) { const float d = f[e] - mean; s2 = fmaf(d, d, s2); }
+        }
     }
-    const float dm = s1 / dim;
-    const float mean = pivot + dm;
-    const float rstd = rsqrtf(fmaxf(s2 / dim - dm * dm, 0.f) + eps);
+    const float rstd = rsqrtf(warp_sum(s2) / dim + eps);
     keep_packed(raw);
     T* orow = out + row * ldo;
 #pragma unroll

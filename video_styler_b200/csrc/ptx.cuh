@@ -16,9 +16,6 @@ namespace wvd {
 // --------------------------------------------------------------------------------------------
 static __device__ unsigned long long g_diag[8];   // [0]=timeout count, [1]=last tag, [2]=block, [3]=thread
 
-#ifndef WVD_WAIT_TIMEOUT_NS
-#define WVD_WAIT_TIMEOUT_NS 4000000000ull
-#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -82,21 +79,21 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
         "selp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
     return ok != 0;
 }
-// Bounded wait.  `tag` identifies the call site in the diagnostic record.
+// Bounded wait.  `tag` identifies the call site in the diagnostic record.  Kept to a handful of instructions: the
+// warp-specialised kernels call this from a dozen sites and their hot loops have to fit the instruction cache.
+// Each probe sleeps in hardware for up to WVD_WAIT_PROBE_NS; 2^22 failed probes (0.2 s .. 8 s) is a deadlock.
+#ifndef WVD_WAIT_PROBE_NS
+#define WVD_WAIT_PROBE_NS 2000
+#endif
+static __device__ __noinline__ void mbar_timeout(uint32_t tag) {
+    atomicAdd(&g_diag[0], 1ull);
+    g_diag[1] = tag; g_diag[2] = blockIdx.x; g_diag[3] = threadIdx.x;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag) {
-    if (mbar_try_wait(bar, parity)) return;
-    uint64_t t0 = 0;
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ff) == 0) {
-            uint64_t now = globaltimer_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > WVD_WAIT_TIMEOUT_NS) {
-                atomicAdd(&g_diag[0], 1ull);
-                g_diag[1] = tag; g_diag[2] = blockIdx.x; g_diag[3] = threadIdx.x;
-                return;
-            }
-        }
+#pragma unroll 1
+    while (!mbar_try_wait_hint(bar, parity, WVD_WAIT_PROBE_NS)) {
+        if (++spins == (1u << 22)) { mbar_timeout(tag); return; }
     }
 }
 
@@ -244,6 +241,13 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+        : "memory");
+}
+
 template <int RegCount>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RegCount)); }
 template <int RegCount>
@@ -251,6 +255,19 @@ __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ uint32_t ld_shared_volatile_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // ---------------------------------------- small math helpers ----------------------------------------
