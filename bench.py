@@ -32,6 +32,20 @@ sys.path.insert(0, ROOT)
 METRIC = "wan_vace_14b_dit_s_per_denoise_step_832x480x73"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE self-attention launch at c3, from the committed
+    `ncu --set full` capture summary (profiles/, written by tools/ncu_summary.py).  None if the summary is absent."""
+    p = os.path.join(ROOT, "profiles", "r1_attention_c3_v2.txt")
+    if not os.path.exists(p):
+        return None
+    tot, mult = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for ln in open(p):
+        f = ln.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(f[2].replace(",", "")) * mult.get(f[1], 1.0)
+    return tot or None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -258,7 +272,10 @@ def main():
                     clocks=clocks,
                     roofline=dict(bound="tensor", kernel="wvd::attn::attention_fwd_kernel (self-attention)",
                                   achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s",
-                                  frac=(achieved / pk["bf16_sustained"]) if achieved else None, traffic=None,
+                                  frac=(achieved / pk["bf16_sustained"]) if achieved else None,
+                                  traffic=ncu_traffic_bytes() if args.workload == "c3" and world == 1 else None,
+                                  traffic_unit="bytes per launch (dram read + write, ncu --set full, profiles/r1_attention_c3_v2.txt); "
+                                               "algorithmic minimum 4*A = 1.214e9 (q, k, v read + out written once)",
                                   peak_source=f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
                                   launches_timed=len(att), avg_launch_ms=att_ms,
                                   flops_per_launch=att_flops,

@@ -7,14 +7,15 @@
 //   warps 0-7 / 8-15    softmax warps of Q tile 0 / 1.  TWO threads per query row (warps w and w+4 of a tile share a
 //                       TMEM lane quarter and a scheduler): each owns 64 of the 128 score columns of its row.  A lone
 //                       warp cannot keep the MUFU pipe busy (in-order issue exposes the MUFU latency: ~70 % of the
-//                       16 exp2/clk/SM); two warps per scheduler can, so a tile's exponentials run at the full rate
-//                       and the two tiles TAKE TURNS on the pipe (named barriers) -- one tile's exponentials overlap the
+//                       16 exp2/clk/SM, tools/microbench/softmax_chunks.cu); with four softmax warps per scheduler
+//                       the pipe is fed whenever either tile has scores, and one tile's exponentials overlap the
 //                       other tile's PV / QK^T on the tensor core.
-//                       exp2 runs against a STALE reference maximum: the row maximum of the tile is computed in the
-//                       issue slots the MUFU stream leaves free, exchanged between the two threads of the row through
-//                       shared memory, and only guards against overflow (the reference moves when exceeded by 2^8).
-//                       P (bf16) goes back to TMEM over the S columns in two hand-overs of 64 keys so that PV of the
-//                       first overlaps the exponentials of the second; row sums in fp32; final O / l -> global.
+//                       exp2 runs against a STALE reference maximum: the row maximum of the tile is exchanged between
+//                       the two threads of the row through shared memory and only guards against overflow (the
+//                       reference moves when exceeded by 2^8, which also bounds how often O is rescaled).
+//                       P (bf16) goes back to TMEM over the S columns in groups of 16 columns and is handed to the
+//                       tensor core in two hand-overs so that PV of the first overlaps the exponentials of the
+//                       second; row sums in fp32; final O / l -> global.
 //   warp 16 (1 thread)  TMA producer: Q tiles once, then K_j, V_j (128x128 bf16, 128-byte swizzle) through a 4-slot ring
 //   warp 17 (1 thread)  MMA issuer  : S_i = Q_i K_j^T   (SS, K-major A and B, 128x128x16 x8) -> TMEM
 //                                     O_i += P_i V_j    (TS: P from TMEM, V MN-major from smem, 128x128x16 x8) -> TMEM
@@ -55,11 +56,15 @@ constexpr int SMEM_BYTES = QT * TILE_BYTES + SLOTS * TILE_BYTES + BAR_BYTES + XC
 constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);   // A = Q (K-major), B = K (K-major)
 constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 128, 0, 1);   // A = P (TMEM), B = V (MN-major)
 #ifndef WVD_ATTN_HO0_GROUPS
-#define WVD_ATTN_HO0_GROUPS 3
+#define WVD_ATTN_HO0_GROUPS 2
 #endif
 #ifndef WVD_ATTN_RELEASE_GROUP
 #define WVD_ATTN_RELEASE_GROUP 3
 #endif
+#ifndef WVD_ATTN_TURNS
+#define WVD_ATTN_TURNS 0
+#endif
+constexpr bool TURNS = WVD_ATTN_TURNS != 0;             // make the two tiles take strict turns on the MUFU pipe (measured 3 % slower than free-running, tools/attn_ab.py)
 constexpr int GC = 16;                                  // columns per exp2 / store group (4 groups per thread)
 constexpr int HO0_GROUPS = WVD_ATTN_HO0_GROUPS;         // groups in the first hand-over of P (the rest form the second)
 constexpr int RELEASE_GROUP = WVD_ATTN_RELEASE_GROUP;   // the other tile's turn starts once this group's exponentials are issued
@@ -260,7 +265,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         float m = -INFINITY;
         float l = 0.f;                              // sum over MY columns
 
-        if (i == 1) named_bar_arrive(1, 2 * (BQ * 2));      // tile 0 takes the first turn
+        if (TURNS && i == 1) named_bar_arrive(1, 2 * (BQ * 2));      // tile 0 takes the first turn
 #ifdef WVD_ATTN_PROF
         const bool prof = p.prof != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && lane == 0;
         uint32_t pc_wait = 0, pc_ld = 0, pc_turn = 0, pc_max = 0, pc_b = 0, pc_redo = 0, pc_x1 = 0, pc_x2 = 0, pt = 0;
@@ -327,8 +332,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             // My tile's turn on the MUFU pipe.  BAR.SYNC is deferred-blocking: the warp only stops at the next
             // instruction that depends on barrier-protected memory, so the exponentials are made to depend on a
             // (zero) word read after it.
-            named_bar_sync(1 + i, 2 * (BQ * 2));
-            const float turn_zero = __uint_as_float(ld_shared_volatile_u32(turn_word));
+            float turn_zero = 0.f;
+            if (TURNS) {
+                named_bar_sync(1 + i, 2 * (BQ * 2));
+                turn_zero = __uint_as_float(ld_shared_volatile_u32(turn_word));
+            }
 #ifdef WVD_ATTN_PROF
             if (prof) { const uint32_t t = clk32() + __float_as_uint(turn_zero); pc_turn += t - pt; pt = t; }
 #endif
@@ -346,7 +354,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     case 2: lsum += exp_chunk<NS, 2 * GC, 3 * GC, EMU_OF_4>(s, pk, sl2_2, negm_2); break;
                     default: lsum += exp_chunk<NS, 3 * GC, 4 * GC, EMU_OF_4>(s, pk, sl2_2, negm_2); break;
                 }
-                if (g == RELEASE_GROUP && (i == 0 || j + 1 < n_kv)) named_bar_arrive(2 - i, 2 * (BQ * 2));   // the other tile's turn
+                if (TURNS && g == RELEASE_GROUP && (i == 0 || j + 1 < n_kv)) named_bar_arrive(2 - i, 2 * (BQ * 2));   // the other tile's turn
                 store_p<GC / 2>(p_tmem + g * (GC / 2), pk);
                 if (g == HO0_GROUPS - 1 || g == NS / GC - 1) {
                     // hand-over; the other warp of my scheduler keeps the MUFU pipe busy meanwhile

@@ -79,11 +79,14 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
         "selp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
     return ok != 0;
 }
-// Bounded wait.  `tag` identifies the call site in the diagnostic record.  Kept to a handful of instructions: the
-// warp-specialised kernels call this from a dozen sites and their hot loops have to fit the instruction cache.
-// Each probe sleeps in hardware for up to WVD_WAIT_PROBE_NS; 2^22 failed probes (0.2 s .. 8 s) is a deadlock.
-#ifndef WVD_WAIT_PROBE_NS
-#define WVD_WAIT_PROBE_NS 2000
+// Bounded wait.  `tag` identifies the call site in the diagnostic record.  Kept small: the warp-specialised kernels
+// call this from a dozen sites and their hot loops have to fit the instruction cache.  The probe is the plain
+// try_wait (SYNCS...TRYWAIT: the warp sleeps in hardware until the phase flips or an implementation-defined limit
+// expires); the form with a suspend-time hint compiles to a NANOSLEEP polling loop that wakes ~16 times per wait and
+// steals issue slots from the warps that are working (ncu source page, profiles/).  Deadlock guard: wall clock every
+// 64 failed probes.
+#ifndef WVD_WAIT_TIMEOUT_NS
+#define WVD_WAIT_TIMEOUT_NS 4000000000ull
 #endif
 static __device__ __noinline__ void mbar_timeout(uint32_t tag) {
     atomicAdd(&g_diag[0], 1ull);
@@ -91,9 +94,14 @@ static __device__ __noinline__ void mbar_timeout(uint32_t tag) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag) {
     uint32_t spins = 0;
+    uint64_t t0 = 0;
 #pragma unroll 1
-    while (!mbar_try_wait_hint(bar, parity, WVD_WAIT_PROBE_NS)) {
-        if (++spins == (1u << 22)) { mbar_timeout(tag); return; }
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 63u) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (spins == 64u) t0 = now;
+            else if (now - t0 > WVD_WAIT_TIMEOUT_NS) { mbar_timeout(tag); return; }
+        }
     }
 }
 
