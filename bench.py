@@ -151,6 +151,13 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def exchange_kind():
+    from video_styler_b200 import ulysses
+    kinds = {type(e).__name__ for e in ulysses._EXCHANGES.values()}
+    return {"P2PUlyssesExchange": "all-to-alls fused into the pack / attention kernels over NVLink peer memory",
+            "UlyssesExchange": "NCCL all_to_all_single"}.get(next(iter(kinds), ""), "none")
+
+
 def workload_name(key, tokens):
     return {"c3": f"c3: Wan2.1-VACE-14B DiT + merged rank-128 Ditto-LoRA stand-in, VACE context, 73 frames 832x480 ({tokens} tokens), one model_fn_wan_video call",
             "c2": f"c2: Wan2.1-T2V-1.3B DiT bf16, 81 frames 832x480 ({tokens} tokens), one model_fn_wan_video call",
@@ -215,12 +222,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = []
+
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         for _ in range(k):
             fn()
+        host_ms.append((time.perf_counter() - h0) * 1e3 / k)       # host time to ENQUEUE one step (no sync inside)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -260,7 +271,7 @@ def main():
                     ms_per_step=ms, higher_is_better=False, scaling="strong", vs_baseline=None, dtype="bf16",
                     data="synthetic", impl="wvd",
                     config=dict(workload=workload_name(args.workload, tokens), tokens=tokens,
-                                parallelism=f"ulysses{world}" if world > 1 else "single",
+                                parallelism=(f"ulysses{world} ({exchange_kind()})" if world > 1 else "single"),
                                 l2="inputs larger than L2: the 34.6 GB of weights are streamed from HBM every step",
                                 step="one model_fn_wan_video call; the default CFG denoising step is two"),
                     tokens_per_s=tokens / (ms / 1e3),
@@ -268,7 +279,7 @@ def main():
                     tc_frac_of_measured_burst=full_flops / (ms / 1e3) / 1e12 / world / pk["bf16_burst"],
                     e2e=dict(value=ms_e2e / 1e3, unit="s", h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=out_host.numel() * 2),
-                    gpu_launches=launches,
+                    gpu_launches=launches, host_enqueue_ms_per_step=host_ms[0],
                     clocks=clocks,
                     roofline=dict(bound="tensor", kernel="wvd::attn::attention_fwd_kernel (self-attention)",
                                   achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s",

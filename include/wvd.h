@@ -113,6 +113,23 @@ int wvd_ulysses_pack_qkv(const void* qkv, int64_t ld, void* send, int64_t n_loca
 int wvd_ulysses_unpack_out(const void* recv, void* out, int64_t ldo, int64_t n_local, int heads, int head_dim,
                            int world, wvd_stream_t stream);
 
+/* ---- C2: Ulysses exchange fused into the producing kernels over NVLink peer memory ---------------------
+ * Replaces the two all-to-alls of xfuser's SeqAllToAll4D (behind usp_attn_forward,
+ * diffsynth/distributed/xdit_context_parallel.py:110-131) with direct peer stores: the pointers are those of a
+ * symmetric-memory rendezvous (one buffer per rank, same size everywhere); the caller orders the steps with two
+ * cross-rank barriers per attention (after the scatter, after the attention).
+ *   scatter_qkv : the pack above, with each destination's chunk stored into THAT rank's receive buffer
+ *                 recv_ptrs[dest][(rank*n_local + row)][3][heads/P][128]  (what its attention reads in place)
+ *   attention_fwd_scatter : wvd_attention_fwd over the local heads and all tokens whose epilogue stores query row t
+ *                 into out_ptrs[t / rows_per_peer] at local row t % rows_per_peer, columns
+ *                 [col_offset, col_offset + num_heads*128) of a (rows_per_peer, ldo) buffer -- the o-projection input. */
+#define WVD_MAX_PEERS 8
+int wvd_ulysses_scatter_qkv(const void* qkv, int64_t ld, void* const* recv_ptrs, int64_t n_local, int heads,
+                            int head_dim, int world, int rank, wvd_stream_t stream);
+int wvd_attention_fwd_scatter(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                              void* const* out_ptrs, int64_t ldo, int64_t rows_per_peer, int64_t col_offset, int world,
+                              int num_heads, int64_t sq, int64_t sk, int head_dim, float scale, wvd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

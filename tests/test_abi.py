@@ -52,6 +52,11 @@ def test_argument_validation_without_gpu():
     assert rc == -1
     rc = lib.wvd_ulysses_pack_qkv(p, 3 * 5 * 128, p, 4, 5, 128, 2, None)                 # heads not divisible
     assert rc == -1 and b"divide" in lib.wvd_last_error()
+    ptrs = (ctypes.c_void_p * 8)(*([p] * 8))
+    rc = lib.wvd_ulysses_scatter_qkv(p, 3 * 4 * 128, ptrs, 4, 4, 128, 9, 0, None)             # more than WVD_MAX_PEERS ranks
+    assert rc == -1 and b"world" in lib.wvd_last_error()
+    rc = lib.wvd_attention_fwd_scatter(p, 128, p, 128, p, 128, ptrs, 256, 4, 200, 2, 1, 8, 8, 128, 0.1, None)   # columns past ldo
+    assert rc == -1 and b"col_offset" in lib.wvd_last_error()
     # empty inputs are accepted as no-ops
     assert lib.wvd_ln_modulate(p, 256, None, None, None, None, p, 256, 0, 256, 1e-6, 0, None) == 0
     assert lib.wvd_scale_add(p, p, 1.0, p, 0, 0, None) == 0

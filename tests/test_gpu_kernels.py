@@ -228,6 +228,40 @@ def test_ulysses_layout_kernels():
     assert torch.equal(ops.ulysses_unpack_out(recv.to(DEV), heads, world).cpu(), cpu_backend.ulysses_unpack_out(recv, heads, world))
 
 
+def test_ulysses_peer_scatter_kernels_match_the_collective_layouts():
+    """The fused exchange (peer stores) against the pack / unpack layouts, with the 'peers' being local buffers: what
+    rank r scatters must land where pack + all_to_all would have put it, and attention_scatter must leave every query
+    row where attention + all_to_all + unpack would have (ragged token count included)."""
+    from tests import cpu_backend
+    world, heads, n_loc = 2, 4, 37
+    hl, w = heads // world, (heads // world) * 128
+    g = torch.Generator().manual_seed(5)
+    qkv = [torch.randn(n_loc, 3 * heads * 128, generator=g).bfloat16() for _ in range(world)]
+    recv = [torch.zeros(world * n_loc, 3 * w, dtype=torch.bfloat16, device=DEV) for _ in range(world)]
+    for r in range(world):
+        ops.ulysses_scatter_qkv(qkv[r].to(DEV), heads, [t.data_ptr() for t in recv], r)
+    torch.cuda.synchronize()
+    packed = [cpu_backend.ulysses_pack_qkv(q, heads, world) for q in qkv]          # (world, n_loc, 3, hl, 128) per source
+    for d in range(world):
+        want = torch.stack([packed[src][d] for src in range(world)]).reshape(world * n_loc, 3 * w)   # all_to_all_single
+        assert torch.equal(recv[d].cpu(), want)
+    # return trip: 70 real tokens (the last shard is padded by 4 rows), every rank attends its heads over all tokens
+    n = world * n_loc - 4
+    outs = [torch.zeros(n_loc, heads * 128, dtype=torch.bfloat16, device=DEV) for _ in range(world)]
+    for r in range(world):
+        rv = recv[r]
+        ops.attention_scatter(rv[:n, :w], rv[:n, w:2 * w], rv[:n, 2 * w:], hl, [t.data_ptr() for t in outs], heads * 128,
+                              n_loc, r * w)
+    torch.cuda.synchronize()
+    for r in range(world):
+        rv = recv[r]
+        full = torch.zeros(world * n_loc, w, dtype=torch.bfloat16, device=DEV)
+        ops.attention(rv[:n, :w], rv[:n, w:2 * w], rv[:n, 2 * w:], hl, out=full[:n])
+        for d in range(world):
+            assert torch.equal(outs[d][:, r * w:(r + 1) * w], full[d * n_loc:(d + 1) * n_loc]), (r, d)
+    _no_timeouts()
+
+
 def test_empty_and_invalid_inputs():
     x = torch.empty(0, 256, dtype=torch.bfloat16, device=DEV)
     assert ops.ln_modulate(x, eps=1e-6).shape == (0, 256)

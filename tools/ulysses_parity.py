@@ -37,7 +37,11 @@ cos = float(torch.nn.functional.cosine_similarity(sharded.double().flatten(), si
 ref = sharded.clone()
 dist.broadcast(ref, 0)
 same = bool(torch.equal(ref, sharded))
-print(f"rank {rank}/{world}: ulysses vs single-GPU rel_l2 {rel:.3e} cos {cos:.7f} max_abs {float(d.abs().max()):.3e} identical_across_ranks {same}", flush=True)
+from video_styler_b200 import ulysses as _U  # noqa: E402
+kind = ",".join(sorted({type(e).__name__ for e in _U._EXCHANGES.values()}))
+print(f"rank {rank}/{world} [{kind}]: ulysses vs single-GPU rel_l2 {rel:.3e} cos {cos:.7f} max_abs {float(d.abs().max()):.3e} identical_across_ranks {same}", flush=True)
+bit = bool(torch.equal(sharded, single))
+print(f"rank {rank}: bit-identical to single-GPU: {bit}", flush=True)
 ok = rel <= 1e-2 and cos >= 0.999 and same
 dist.barrier()
 dist.destroy_process_group()

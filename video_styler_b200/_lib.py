@@ -34,7 +34,11 @@ SIGNATURES = {
                               c_int64, c_int64, c_int, c_float, c_void_p],
     "wvd_ulysses_pack_qkv": [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
     "wvd_ulysses_unpack_out": [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p],
+    "wvd_ulysses_scatter_qkv": [c_void_p, c_int64, ctypes.POINTER(c_void_p), c_int64, c_int, c_int, c_int, c_int, c_void_p],
+    "wvd_attention_fwd_scatter": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, ctypes.POINTER(c_void_p), c_int64,
+                                  c_int64, c_int64, c_int, c_int, c_int64, c_int64, c_int, c_float, c_void_p],
 }
+MAX_PEERS = 8
 
 WVD_BF16, WVD_F32 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_GATE_RES = 0, 1, 2, 3

@@ -73,6 +73,10 @@ constexpr float REF_MARGIN = 8.0f;    // log2 units: the softmax reference point
 struct Params {
     __nv_bfloat16* out;
     long long ldo;
+    // Ulysses return trip fused into the epilogue: query row `row` belongs to rank row / rows_per_peer and is stored
+    // straight into that rank's buffer (peer pointer, NVLink) at local row row % rows_per_peer; 0 = single output.
+    __nv_bfloat16* out_peer[WVD_MAX_PEERS];
+    int rows_per_peer;
     int sq, sk, n_kv;
     float scale_log2;
     unsigned long long* prof;   // optional device buffer (developer profiling, -DWVD_ATTN_PROF builds only)
@@ -381,7 +385,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const float inv_l = 1.0f / (l + __uint_as_float(ld_shared_volatile_u32(xchg_other(0))));
         mbar_wait(o_full(i), 0, 0x310 + i);
         tc_fence_after();
-        __nv_bfloat16* orow = p.out + static_cast<long long>(row) * p.ldo + head * HD + h * (HD / 2);
+        __nv_bfloat16* orow;
+        if (p.rows_per_peer > 0) {
+            const int dest = row / p.rows_per_peer;
+            orow = p.out_peer[dest < WVD_MAX_PEERS ? dest : 0] + static_cast<long long>(row - dest * p.rows_per_peer) * p.ldo;
+        } else {
+            orow = p.out + static_cast<long long>(row) * p.ldo;
+        }
+        orow += head * HD + h * (HD / 2);
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
@@ -423,12 +434,13 @@ extern "C" __attribute__((visibility("default"))) int wvd_debug_attention_profil
     return WVD_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int wvd_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                                 void* out, int64_t ldo, int num_heads, int64_t sq, int64_t sk, int head_dim,
-                                 float scale, wvd_stream_t stream) {
-    using namespace wvd;
-    WVD_REQUIRE(q && k && v && out, "wvd_attention_fwd: null pointer");
-    WVD_REQUIRE(head_dim == attn::HD, "wvd_attention_fwd: head_dim must be 128 (got %d)", head_dim);
+namespace wvd {
+namespace attn {
+static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                  void* const* out_peers, int world, int64_t rows_per_peer, int64_t ldo, int num_heads, int64_t sq,
+                  int64_t sk, int head_dim, float scale, wvd_stream_t stream) {
+    WVD_REQUIRE(q && k && v && (out || out_peers), "wvd_attention_fwd: null pointer");
+    WVD_REQUIRE(head_dim == HD, "wvd_attention_fwd: head_dim must be 128 (got %d)", head_dim);
     WVD_REQUIRE(num_heads > 0 && num_heads <= 65535, "wvd_attention_fwd: bad num_heads %d", num_heads);
     WVD_REQUIRE(sq > 0 && sk > 0 && sq < (1ll << 31) && sk < (1ll << 31), "wvd_attention_fwd: bad sequence lengths sq=%lld sk=%lld", (long long)sq, (long long)sk);
     const int64_t width = (int64_t)num_heads * head_dim;
@@ -437,38 +449,74 @@ extern "C" __attribute__((visibility("default"))) int wvd_attention_fwd(const vo
     WVD_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) && ((uintptr_t)out % 16 == 0),
                 "wvd_attention_fwd: pointers must be 16-byte aligned");
     CUtensorMap tmQ, tmK, tmV;
-    int rc = get_tensor_map_bf16(&tmQ, q, (uint64_t)sq, (uint64_t)width, (uint64_t)ldq, attn::BQ);
+    int rc = get_tensor_map_bf16(&tmQ, q, (uint64_t)sq, (uint64_t)width, (uint64_t)ldq, BQ);
     if (rc) return rc;
-    rc = get_tensor_map_bf16(&tmK, k, (uint64_t)sk, (uint64_t)width, (uint64_t)ldk, attn::BKV);
+    rc = get_tensor_map_bf16(&tmK, k, (uint64_t)sk, (uint64_t)width, (uint64_t)ldk, BKV);
     if (rc) return rc;
-    rc = get_tensor_map_bf16(&tmV, v, (uint64_t)sk, (uint64_t)width, (uint64_t)ldv, attn::BKV);
+    rc = get_tensor_map_bf16(&tmV, v, (uint64_t)sk, (uint64_t)width, (uint64_t)ldv, BKV);
     if (rc) return rc;
-    attn::Params p;
+    Params p;
     p.out = (__nv_bfloat16*)out;
     p.ldo = ldo;
+    p.rows_per_peer = 0;
+    for (int r = 0; r < WVD_MAX_PEERS; ++r) p.out_peer[r] = nullptr;
+    if (out_peers != nullptr) {
+        WVD_REQUIRE(world >= 1 && world <= WVD_MAX_PEERS && rows_per_peer > 0 && rows_per_peer < (1ll << 31) &&
+                    rows_per_peer * world >= sq, "wvd_attention_fwd_scatter: bad world / rows_per_peer");
+        for (int r = 0; r < world; ++r) {
+            WVD_REQUIRE(out_peers[r] && ((uintptr_t)out_peers[r] % 16 == 0), "wvd_attention_fwd_scatter: bad output pointer of rank %d", r);
+            p.out_peer[r] = (__nv_bfloat16*)out_peers[r];
+        }
+        p.rows_per_peer = (int)rows_per_peer;
+    }
     p.sq = (int)sq;
     p.sk = (int)sk;
-    p.n_kv = (int)((sk + attn::BKV - 1) / attn::BKV);
+    p.n_kv = (int)((sk + BKV - 1) / BKV);
     p.scale_log2 = scale * 1.4426950408889634f;
-    p.prof = attn::g_prof_buffer;
+    p.prof = g_prof_buffer;
     static int emu = -1;
     if (emu < 0) {
         const char* e = getenv("WVD_ATTN_EMU");        // tuning knob: 0..3 of every 4 column pairs on the FMA pipes
-        int v = e ? atoi(e) : 0;          // measured on B200: 0 is fastest (the FMA-pipe polynomial costs ~16 cycles/element)
-        emu = v < 0 ? 0 : (v > 3 ? 3 : v);
-        WVD_CHECK_CUDA(cudaFuncSetAttribute(attn::attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-        WVD_CHECK_CUDA(cudaFuncSetAttribute(attn::attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-        WVD_CHECK_CUDA(cudaFuncSetAttribute(attn::attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-        WVD_CHECK_CUDA(cudaFuncSetAttribute(attn::attention_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+        int ev = e ? atoi(e) : 0;          // measured on B200: 0 is fastest (the softmax is issue-bound, not MUFU-bound)
+        emu = ev < 0 ? 0 : (ev > 3 ? 3 : ev);
+        WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     }
-    dim3 grid((unsigned)((sq + attn::QT * attn::BQ - 1) / (attn::QT * attn::BQ)), (unsigned)num_heads);
+    dim3 grid((unsigned)((sq + QT * BQ - 1) / (QT * BQ)), (unsigned)num_heads);
     cudaStream_t st = (cudaStream_t)stream;
     switch (emu) {
-        case 0: attn::attention_fwd_kernel<0><<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-        case 1: attn::attention_fwd_kernel<1><<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-        case 2: attn::attention_fwd_kernel<2><<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-        default: attn::attention_fwd_kernel<3><<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+        case 0: attention_fwd_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+        case 1: attention_fwd_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+        case 2: attention_fwd_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+        default: attention_fwd_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
     }
     WVD_CHECK_CUDA(cudaGetLastError());
     return WVD_OK;
+}
+}  // namespace attn
+}  // namespace wvd
+
+extern "C" __attribute__((visibility("default"))) int wvd_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                 void* out, int64_t ldo, int num_heads, int64_t sq, int64_t sk, int head_dim,
+                                 float scale, wvd_stream_t stream) {
+    WVD_REQUIRE(out, "wvd_attention_fwd: null pointer");
+    return wvd::attn::launch(q, ldq, k, ldk, v, ldv, out, nullptr, 1, 0, ldo, num_heads, sq, sk, head_dim, scale, stream);
+}
+
+// Ulysses return trip fused into the attention epilogue: out_ptrs[r] is rank r's (rows_per_peer, ldo) output buffer
+// (peer pointers); query row t is stored at out_ptrs[t / rows_per_peer] + (t % rows_per_peer) * ldo + col_offset.
+extern "C" __attribute__((visibility("default"))) int wvd_attention_fwd_scatter(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                         int64_t ldv, void* const* out_ptrs, int64_t ldo, int64_t rows_per_peer,
+                                         int64_t col_offset, int world, int num_heads, int64_t sq, int64_t sk,
+                                         int head_dim, float scale, wvd_stream_t stream) {
+    WVD_REQUIRE(out_ptrs && world >= 1 && world <= WVD_MAX_PEERS, "wvd_attention_fwd_scatter: bad peers");
+    WVD_REQUIRE(col_offset >= 0 && col_offset % 8 == 0 && col_offset + (int64_t)num_heads * head_dim <= ldo,
+                "wvd_attention_fwd_scatter: bad col_offset");
+    void* shifted[WVD_MAX_PEERS];
+    for (int r = 0; r < world; ++r) shifted[r] = out_ptrs[r] ? (void*)((__nv_bfloat16*)out_ptrs[r] + col_offset) : nullptr;
+    // the leading-dimension check of launch() is against the local head count only
+    return wvd::attn::launch(q, ldq, k, ldk, v, ldv, nullptr, shifted, world, rows_per_peer, ldo, num_heads, sq, sk, head_dim,
+                             scale, stream);
 }

@@ -351,6 +351,30 @@ ulysses_pack_kernel(const uint4* __restrict__ qkv, long long ld_vec, uint4* __re
     }
 }
 
+// Fused pack + all-to-all: the same gather as ulysses_pack_kernel, but each destination's chunk is stored straight into
+// THAT rank's receive buffer over NVLink (peer pointers from a symmetric-memory rendezvous), in the layout the attention
+// kernel reads: recv_dest[(rank*n_local + row)][which][hl][c].  1,280-byte contiguous runs per (dest,row,which) at P = 8.
+struct PeerPtrs { uint4* p[WVD_MAX_PEERS]; };
+__global__ void __launch_bounds__(256)
+ulysses_scatter_kernel(const uint4* __restrict__ qkv, long long ld_vec, PeerPtrs recv, long long n_local, int heads,
+                       int hd_vec, int world, int rank) {
+    const int hl_n = heads / world;
+    const long long per_row = 3ll * hl_n * hd_vec;                  // vectors per (dest,row)
+    const long long total = static_cast<long long>(world) * n_local * per_row;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % hd_vec);
+        long long t = i / hd_vec;
+        const int hl = static_cast<int>(t % hl_n); t /= hl_n;
+        const int which = static_cast<int>(t % 3); t /= 3;
+        const long long row = t % n_local;
+        const int dest = static_cast<int>(t / n_local);
+        const long long src = row * ld_vec + (static_cast<long long>(which) * heads + dest * hl_n + hl) * hd_vec + c;
+        const long long dst = (static_cast<long long>(rank) * n_local + row) * per_row + (static_cast<long long>(which) * hl_n + hl) * hd_vec + c;
+        recv.p[dest][dst] = qkv[src];
+    }
+}
+
 // out[row][src*Dl + c] = recv[src][row][c]
 __global__ void __launch_bounds__(256)
 ulysses_unpack_kernel(const uint4* __restrict__ recv, uint4* __restrict__ out, long long ldo_vec, long long n_local,
@@ -492,6 +516,25 @@ extern "C" __attribute__((visibility("default"))) int wvd_ulysses_pack_qkv(const
     const long long total = (long long)n_local * 3 * heads * (head_dim / 8);
     ew::ulysses_pack_kernel<<<ew::stream_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)qkv, ld / 8, (uint4*)send, n_local, heads, head_dim / 8, world);
+    WVD_CHECK_CUDA(cudaGetLastError());
+    return WVD_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_ulysses_scatter_qkv(const void* qkv, int64_t ld, void* const* recv_ptrs, int64_t n_local, int heads,
+                                       int head_dim, int world, int rank, wvd_stream_t stream) {
+    WVD_REQUIRE(world >= 1 && world <= WVD_MAX_PEERS && rank >= 0 && rank < world, "wvd_ulysses_scatter_qkv: bad world/rank %d/%d", world, rank);
+    WVD_REQUIRE(heads > 0 && heads % world == 0, "wvd_ulysses_scatter_qkv: heads (%d) must divide by world (%d)", heads, world);
+    WVD_REQUIRE(head_dim % 8 == 0 && ld % 8 == 0 && ld >= 3ll * heads * head_dim, "wvd_ulysses_scatter_qkv: bad head_dim/ld");
+    if (n_local == 0) return WVD_OK;
+    WVD_REQUIRE(qkv && recv_ptrs && n_local > 0 && aligned16(qkv), "wvd_ulysses_scatter_qkv: bad pointers");
+    ew::PeerPtrs pp;
+    for (int r = 0; r < WVD_MAX_PEERS; ++r) {
+        pp.p[r] = r < world ? (uint4*)recv_ptrs[r] : nullptr;
+        WVD_REQUIRE(r >= world || (pp.p[r] && aligned16(pp.p[r])), "wvd_ulysses_scatter_qkv: bad receive pointer of rank %d", r);
+    }
+    const long long total = (long long)n_local * 3 * heads * (head_dim / 8);
+    ew::ulysses_scatter_kernel<<<ew::stream_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)qkv, ld / 8, pp, n_local, heads, head_dim / 8, world, rank);
     WVD_CHECK_CUDA(cudaGetLastError());
     return WVD_OK;
 }

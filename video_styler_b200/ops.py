@@ -240,3 +240,48 @@ def ulysses_unpack_out(recv: Tensor, heads: int, world: int, out: Optional[Tenso
     check(_lib.load().wvd_ulysses_unpack_out(recv.data_ptr(), out.data_ptr(), _ld(out), n, heads, 128, world, _stream()),
           "wvd_ulysses_unpack_out")
     return out
+
+
+def _ptr_array(ptrs):
+    import ctypes
+    arr = (ctypes.c_void_p * _lib.MAX_PEERS)()
+    for i, v in enumerate(ptrs):
+        arr[i] = int(v)
+    return arr
+
+
+def ulysses_scatter_qkv(qkv: Tensor, heads: int, recv_ptrs, rank: int) -> None:
+    """Fused pack + all-to-all over NVLink: rank `rank`'s (n_local, 3*heads*128) q|k|v is stored straight into every
+    rank's receive buffer (recv_ptrs: data pointers of a symmetric-memory rendezvous), in the layout its attention
+    reads in place.  The caller issues a cross-rank barrier afterwards."""
+    qkv = _chk2d(qkv, "qkv")
+    world = len(recv_ptrs)
+    if qkv.dtype != torch.bfloat16 or qkv.shape[1] != 3 * heads * 128 or world > _lib.MAX_PEERS:
+        raise WvdError("ulysses_scatter_qkv: bf16 (n, 3*heads*128) and at most 8 ranks expected")
+    check(_lib.load().wvd_ulysses_scatter_qkv(qkv.data_ptr(), _ld(qkv), _ptr_array(recv_ptrs), qkv.shape[0], heads, 128,
+                                              world, rank, _stream()), "wvd_ulysses_scatter_qkv")
+
+
+def attention_scatter(q: Tensor, k: Tensor, v: Tensor, num_heads: int, out_ptrs, ldo: int, rows_per_peer: int,
+                      col_offset: int, scale: Optional[float] = None) -> None:
+    """ops.attention over the local heads whose epilogue stores query row t into rank t // rows_per_peer's
+    (rows_per_peer, ldo) buffer at columns [col_offset, col_offset + num_heads*128) (peer pointers, NVLink): the
+    Ulysses return all-to-all fused into the attention kernel.  The caller issues a cross-rank barrier afterwards."""
+    q, k, v = _chk2d(q, "q"), _chk2d(k, "k"), _chk2d(v, "v")
+    sq, width = q.shape
+    sk = k.shape[0]
+    if q.dtype != torch.bfloat16 or width != num_heads * 128 or k.shape[1] != width or v.shape != k.shape:
+        raise WvdError("attention_scatter: bf16 q/k/v with head_dim 128 expected")
+    if sq == 0:
+        return
+    scale = 1.0 / math.sqrt(128.0) if scale is None else scale
+    prof = PROFILE is not None and sq == sk
+    if prof:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(_lib.load().wvd_attention_fwd_scatter(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v),
+                                                _ptr_array(out_ptrs), ldo, rows_per_peer, col_offset, len(out_ptrs),
+                                                num_heads, sq, sk, 128, scale, _stream()), "wvd_attention_fwd_scatter")
+    if prof:
+        e1.record()
+        PROFILE.setdefault("self_attention", []).append((e0, e1, num_heads, sq))

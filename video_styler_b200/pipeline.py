@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import engine, ops as _cuda_ops
-from .ulysses import UlyssesExchange, shard_bounds
+from .ulysses import make_exchange, shard_bounds
 
 Tensor = torch.Tensor
 
@@ -114,7 +114,7 @@ def model_fn_wan_video(
     if use_unified_sequence_parallel:
         import torch.distributed as dist
         if dist.is_initialized() and dist.get_world_size(sp_group) > 1:
-            exchange = UlyssesExchange(sp_group, n_tokens)
+            exchange = make_exchange(sp_group, n_tokens, x.device)
             lo, hi, n_loc = shard_bounds(n_tokens, exchange.world, exchange.rank)
 
     tea_cache_update = tea_cache.check(dit, x, t_mod) if tea_cache is not None else False

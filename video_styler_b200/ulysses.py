@@ -8,8 +8,16 @@ ulysses_degree = world, ring_degree = 1, wan_video_new.py:318-322) with an in-tr
   heads are sharded: one all-to-all moves q|k|v from (n_loc, 3, H, 128) to (N, 3, H/P, 128), attention runs over
   H/P heads x all N tokens, and the inverse all-to-all returns (n_loc, H*128) for the o-projection.
 
-The pack kernel writes the dest-rank-major send buffer; the receive buffer is consumed in place by the attention
-kernel (strided TMA views), and the attention output is already the return-trip send layout.
+Two implementations of the exchange:
+
+  P2PUlyssesExchange   (default on NVLink boxes) both all-to-alls are FUSED into the kernels on either side of them
+                       and run over peer memory: the pack kernel stores each destination's q|k|v chunk straight into
+                       that rank's receive buffer (wvd_ulysses_scatter_qkv), and the attention kernel's epilogue stores
+                       every query row straight into its owner's o-projection input (wvd_attention_fwd_scatter).  The
+                       buffers come from a torch symmetric-memory rendezvous; two cross-rank barriers per attention
+                       order the steps.  No send/receive staging, no unpack pass, no NCCL launch on the block path.
+  UlyssesExchange      the NCCL baseline (``all_to_all_single``; gloo in the CPU tests): pack kernel -> all-to-all ->
+                       attention on the receive buffer in place -> all-to-all -> unpack kernel.
 Full-width QK-RMSNorm + RoPE run BEFORE the scatter with the rank's global token offset, as the reference does
 (xdit_context_parallel.py:27-40, 110-117).
 """
@@ -62,3 +70,76 @@ class UlyssesExchange(SelfAttnExchange):
         out = torch.empty((self.world * y_loc.shape[0], y_loc.shape[1]), dtype=y_loc.dtype, device=y_loc.device)
         dist.all_gather_into_tensor(out, y_loc.contiguous(), group=self.group)
         return out
+
+
+class P2PUlyssesExchange(UlyssesExchange):
+    """Ulysses exchange with both all-to-alls fused into the producing kernels over NVLink peer memory (see the module
+    docstring).  Bit-identical to UlyssesExchange (same arithmetic, only the data path differs)."""
+
+    def __init__(self, group, n_tokens: int):
+        super().__init__(group, n_tokens)
+        self._bufs = {}
+
+    def _buffers(self, n_loc: int, heads: int, device):
+        key = (n_loc, heads)
+        if key not in self._bufs:
+            import importlib
+            symm_mem = importlib.import_module("torch.distributed._symmetric_memory")
+            p, w = self.world, (heads // self.world) * 128
+            recv = symm_mem.empty((p * n_loc, 3 * w), dtype=torch.bfloat16, device=device)
+            aout = symm_mem.empty((n_loc, heads * 128), dtype=torch.bfloat16, device=device)
+            recv.zero_()
+            aout.zero_()          # rows past the last token (ragged N) are never written: they stay zero
+            grp = self.group if self.group is not None else dist.group.WORLD
+            h_recv = symm_mem.rendezvous(recv, grp)
+            h_out = symm_mem.rendezvous(aout, grp)
+            torch.cuda.synchronize(device)
+            h_recv.barrier(channel=0)
+            self._bufs[key] = (recv, aout, h_recv, h_out, [int(x) for x in h_recv.buffer_ptrs], [int(x) for x in h_out.buffer_ptrs])
+        return self._bufs[key]
+
+    def attend(self, ops, qkv, heads: int, out, ws):
+        p, r = self.world, self.rank
+        if heads % p != 0:
+            raise ValueError(f"Ulysses needs num_heads ({heads}) divisible by the sequence-parallel world size ({p})")
+        n_loc = qkv.shape[0]
+        hl = heads // p
+        w = hl * 128
+        recv, aout, h_recv, h_out, recv_ptrs, out_ptrs = self._buffers(n_loc, heads, qkv.device)
+        # (1) q|k|v -> every rank's receive buffer.  Safe to overwrite: every rank passed the previous barrier (2)
+        #     only after its previous attention had finished reading.
+        ops.ulysses_scatter_qkv(qkv, heads, recv_ptrs, r)
+        h_recv.barrier(channel=0)
+        n = self.n_tokens                       # rows >= n are the zero padding of the last shard: never attended
+        # (2) attention over my heads and all tokens; rows go straight to their owners' o-projection input.  Safe to
+        #     overwrite: every rank entered barrier (1) only after its previous o-projection had been enqueued
+        #     ahead of it on its stream.
+        ops.attention_scatter(recv[:n, :w], recv[:n, w:2 * w], recv[:n, 2 * w:], hl, out_ptrs, heads * 128, n_loc, r * w)
+        h_out.barrier(channel=0)
+        return aout
+
+
+_EXCHANGES = {}
+
+
+def make_exchange(group, n_tokens: int, device) -> UlyssesExchange:
+    """The exchange for this (group, token count): peer-memory fused kernels when the group runs on CUDA with
+    symmetric memory available (WVD_ULYSSES=nccl forces the NCCL baseline), else NCCL / gloo collectives.  Cached:
+    the symmetric-memory rendezvous is a collective and is done once."""
+    import os
+    key = (id(group), n_tokens, str(device))
+    if key in _EXCHANGES:
+        return _EXCHANGES[key]
+    want = os.environ.get("WVD_ULYSSES", "p2p").lower()
+    ex = None
+    if want != "nccl" and torch.device(device).type == "cuda" and dist.get_backend(group) == "nccl":
+        try:
+            import importlib
+            importlib.import_module("torch.distributed._symmetric_memory")
+            ex = P2PUlyssesExchange(group, n_tokens)
+        except Exception:           # no symmetric memory in this torch build: NCCL collectives
+            ex = None
+    if ex is None:
+        ex = UlyssesExchange(group, n_tokens)
+    _EXCHANGES[key] = ex
+    return ex
