@@ -106,6 +106,7 @@ int get_tensor_map_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64
 
 int gemm_read_diag(unsigned long long* out);
 int attn_read_diag(unsigned long long* out);
+int attn_pair_read_diag(unsigned long long* out);
 
 }  // namespace wvd
 
@@ -116,8 +117,10 @@ extern "C" __attribute__((visibility("default"))) int wvd_sm_arch(void) { return
 extern "C" __attribute__((visibility("default"))) int wvd_debug_flags(unsigned long long out[8]) {
     using namespace wvd;
     WVD_CHECK_CUDA(cudaDeviceSynchronize());
-    unsigned long long a[8] = {0}, b[8] = {0};
-    if (gemm_read_diag(a) != 0 || attn_read_diag(b) != 0) return set_error(WVD_ERR_CUDA, "reading diagnostics failed");
+    unsigned long long a[8] = {0}, b[8] = {0}, c[8] = {0};
+    if (gemm_read_diag(a) != 0 || attn_read_diag(b) != 0 || attn_pair_read_diag(c) != 0)
+        return set_error(WVD_ERR_CUDA, "reading diagnostics failed");
+    if (c[0] != 0) { b[0] += c[0]; b[1] = c[1]; b[2] = c[2]; b[3] = c[3]; }      // both attention kernels report as "attn"
     for (int i = 0; i < 8; ++i) out[i] = a[i];
     out[0] = a[0] + b[0];
     if (b[0] != 0) { out[1] = b[1]; out[2] = b[2]; out[3] = b[3]; }

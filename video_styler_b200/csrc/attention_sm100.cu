@@ -435,6 +435,9 @@ extern "C" __attribute__((visibility("default"))) int wvd_debug_attention_profil
 }
 
 namespace wvd {
+int attention_pair_launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                          void* const* out_peers, int world, int64_t rows_per_peer, int64_t ldo, int num_heads,
+                          int64_t sq, int64_t sk, float scale, int emu, cudaStream_t st);
 namespace attn {
 static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                   void* const* out_peers, int world, int64_t rows_per_peer, int64_t ldo, int num_heads, int64_t sq,
@@ -484,8 +487,19 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
         WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     }
-    dim3 grid((unsigned)((sq + QT * BQ - 1) / (QT * BQ)), (unsigned)num_heads);
     cudaStream_t st = (cudaStream_t)stream;
+    static int which = -1;
+    if (which < 0) {
+        const char* e = getenv("WVD_ATTN_KERNEL");     // developer A/B: 2 = experimental CTA-pair kernel (attention_pair_sm100.cu)
+        which = e ? atoi(e) : 0;
+    }
+    // The CTA-pair kernel (one Q tile per CTA, triple-buffered S, K/V multicast across a 2-CTA cluster) measures the
+    // same 14.1-14.3 ms as this kernel at c3 and still has a rare deadlock (1 in ~100 launches, tools/attn_stress.py),
+    // so it is opt-in only.
+    if (which == 2)
+        return attention_pair_launch(q, ldq, k, ldk, v, ldv, out, out_peers ? (void* const*)p.out_peer : nullptr, world,
+                                     rows_per_peer, ldo, num_heads, sq, sk, scale, emu, st);
+    dim3 grid((unsigned)((sq + QT * BQ - 1) / (QT * BQ)), (unsigned)num_heads);
     switch (emu) {
         case 0: attention_fwd_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
         case 1: attention_fwd_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;

@@ -89,8 +89,9 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 #define WVD_WAIT_TIMEOUT_NS 4000000000ull
 #endif
 static __device__ __noinline__ void mbar_timeout(uint32_t tag) {
-    atomicAdd(&g_diag[0], 1ull);
-    g_diag[1] = tag; g_diag[2] = blockIdx.x; g_diag[3] = threadIdx.x;
+    if (atomicAdd(&g_diag[0], 1ull) == 0ull) {      // the FIRST timeout is the culprit, the rest cascade from it
+        g_diag[1] = tag; g_diag[2] = blockIdx.x; g_diag[3] = threadIdx.x;
+    }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag) {
     uint32_t spins = 0;
@@ -144,6 +145,39 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
+}
+
+// ---------------------------------------- thread-block clusters ----------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// all threads of all CTAs of the cluster
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier of another CTA of the cluster (address from mapa_shared).  RELAXED: a release at cluster scope
+// compiles to MEMBAR.ALL.GPU + error barriers, which serialises a TMA producer with its own loads in flight; the
+// callers only signal "I have stopped reading" (established by an acquire wait just before), no data of theirs.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load delivered to the same shared-memory offset of every CTA in cta_mask; each destination CTA's mbarrier
+// (same offset as `bar`) receives the complete_tx of the bytes written to it
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                      uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
 }
 
 // ---------------------------------------- tcgen05 / TMEM ----------------------------------------
