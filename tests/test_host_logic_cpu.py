@@ -153,3 +153,28 @@ def test_unsupported_surface_raises():
         run_model_fn(fix, dit, None, cpu_backend, clip_feature=torch.zeros(1))
     with pytest.raises(NotImplementedError):
         V.WanModel(has_image_input=True, **O.DIT_CONFIGS["tiny"])
+
+
+def test_lora_loader_matches_the_reference_merge():
+    """video_styler_b200.GeneralLoRALoader (mirror of diffsynth/lora/__init__.py:4-45) against the oracle's merge, which
+    tests/golden pins to the REAL loader (tiny_vace_lora was generated with it): same targets found through
+    named_modules(), same W + alpha * B @ A bit for bit, adapter-named and 'diffusion_model.'-prefixed keys included."""
+    import video_styler_b200 as V
+    vcfg = O.VACE_CONFIGS["tiny"]
+    vsd = O.make_state_dict(O.vace_param_shapes(vcfg), seed=3, perturb_norms=True)
+    lsd = O.make_lora_state_dict(vcfg, seed=2, rank=16)
+    vace = V.VaceWanModel(has_image_input=False, **vcfg)
+    vace.load_state_dict({k: v.clone() for k, v in vsd.items()}, strict=True, assign=True)
+    n = V.GeneralLoRALoader(device="cpu", torch_dtype=torch.float32).load(vace, lsd, alpha=0.7)
+    want = {k: v.clone() for k, v in vsd.items()}
+    O.lora_merge(want, lsd, alpha=0.7)
+    assert n == sum(1 for k in lsd if ".lora_B." in k) > 0
+    got = vace.state_dict()
+    changed = 0
+    for k, v in want.items():
+        assert torch.equal(got[k], v), k
+        changed += int(not torch.equal(v, vsd[k]))
+    assert changed == n
+    # key forms of get_name_dict: adapter name optional, 'diffusion_model.' prefix dropped
+    nd = V.GeneralLoRALoader().get_name_dict({"diffusion_model.vace_blocks.0.ffn.0.lora_B.weight": 0, "vace_blocks.1.self_attn.q.lora_B.default.weight": 0})
+    assert set(nd) == {"vace_blocks.0.ffn.0", "vace_blocks.1.self_attn.q"}

@@ -49,3 +49,25 @@ def test_install_on_real_reference_modules_with_vram_wrappers(golden_dir):
                  tea_cache=None, use_unified_sequence_parallel=False, motion_bucket_id=None, cfg_merge=False)
     m = O.parity_metrics(out, fix["output"])
     assert m["max_abs"] <= 5e-5 and m["rel_l2"] <= 2e-5, m
+
+
+def test_lora_loader_equals_the_real_general_lora_loader():
+    """video_styler_b200.GeneralLoRALoader against the reference's own class on the reference's own VaceWanModel:
+    identical merged weights, bit for bit (fp32 and bf16 merge dtypes)."""
+    import video_styler_b200 as V
+    w, dit_mod, vace_mod = ref_shim.load()
+    from diffsynth.lora import GeneralLoRALoader
+    vcfg = O.VACE_CONFIGS["tiny"]
+    lsd = O.make_lora_state_dict(vcfg, seed=2, rank=16)
+    for dt in (torch.float32, torch.bfloat16):
+        sd = O.make_state_dict(O.vace_param_shapes(vcfg), seed=3, perturb_norms=True)
+        ref = vace_mod.VaceWanModel(has_image_input=False, **vcfg)
+        ref.load_state_dict(sd, strict=True)
+        ours = V.VaceWanModel(has_image_input=False, **vcfg)
+        ours.load_state_dict(sd, strict=True)
+        GeneralLoRALoader(device="cpu", torch_dtype=dt).load(ref, lsd, alpha=0.5)
+        V.GeneralLoRALoader(device="cpu", torch_dtype=dt).load(ours, lsd, alpha=0.5)
+        a, b = ref.state_dict(), ours.state_dict()
+        assert a.keys() == b.keys()
+        for k in a:
+            assert torch.equal(a[k], b[k]), (k, dt)

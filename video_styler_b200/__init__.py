@@ -3,9 +3,10 @@
 Host code is Python/PyTorch (device memory, streams, torch.distributed); the math runs in libwvd.so, a C-ABI
 library of hand-written CUDA kernels (include/wvd.h).  Public surface mirrors the reference:
 
-    model_fn_wan_video, WanModel, VaceWanModel, FlowMatchScheduler, denoise, install(pipe)
+    model_fn_wan_video, WanModel, VaceWanModel, FlowMatchScheduler, GeneralLoRALoader / load_lora, denoise, install(pipe)
 """
 from ._lib import WvdError  # noqa: F401
+from .lora import GeneralLoRALoader, load_lora  # noqa: F401
 from .pipeline import FlowMatchScheduler, denoise, install, model_fn_wan_video  # noqa: F401
 from .wan_video_dit import WanModel  # noqa: F401
 from .wan_video_vace import VaceWanModel  # noqa: F401
