@@ -24,6 +24,7 @@
 #include "softmax_math.cuh"
 
 namespace wvd {
+namespace attn { extern unsigned long long* g_prof_buffer; }
 namespace attn2 {
 
 using attn::exp_chunk;
@@ -32,7 +33,10 @@ using attn::store_p;
 
 constexpr int BQ = 128, BKV = 128, HD = 128;
 constexpr int GC = 16;                        // columns per exp2 / store group
-constexpr int HO0_GROUPS = 6;                 // groups of 16 keys in the first hand-over of P (the rest form the second)
+#ifndef WVD_ATTN2_HO0
+#define WVD_ATTN2_HO0 6
+#endif
+constexpr int HO0_GROUPS = WVD_ATTN2_HO0;     // groups of 16 keys in the first hand-over of P (8 = a single hand-over)
 constexpr int TILE_BYTES = 128 * 128 * 2;     // 32 KB
 constexpr int HALF_BYTES = TILE_BYTES / 2;    // one 64-column TMA box of 128 rows
 constexpr int SLOTS = 6;                      // K/V ring: 6 x 32 KB + 32 KB of Q = 224 KB of shared memory
@@ -40,7 +44,7 @@ constexpr int SBUF = 3;                       // S buffers in TMEM
 constexpr int O_COL = SBUF * 128;             // first TMEM column of the O accumulator
 constexpr int SOFTMAX_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9;
 constexpr int NUM_THREADS = 10 * 32;
-constexpr int BAR_BYTES = 256;
+constexpr int BAR_BYTES = 384;
 constexpr int XCHG_BYTES = 3 * BQ * 4;        // m[row], l[warpgroup][row] fp32
 constexpr int SMEM_BYTES = TILE_BYTES + SLOTS * TILE_BYTES + BAR_BYTES + XCHG_BYTES + 1024;
 constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);   // A = Q (K-major), B = K (K-major)
@@ -54,7 +58,14 @@ struct Params {
     int rows_per_peer;
     int sq, sk, n_kv;
     float scale_log2;
+    unsigned long long* prof;   // optional device buffer (developer profiling, -DWVD_ATTN_PROF builds only)
 };
+
+#ifdef WVD_ATTN_PROF
+#define PROF_LAP(acc) do { if (prof) { uint32_t t_; asm volatile("mov.u32 %0, %%clock;" : "=r"(t_)); (acc) += t_ - pt; pt = t_; } } while (0)
+#else
+#define PROF_LAP(acc) do { } while (0)
+#endif
 
 template <int EMU_OF_4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -72,9 +83,13 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     auto kv_cons = [&](int s) { return bar_base + 8 + (SLOTS + s) * 8; };       // MY MMAs have finished reading slot s
     auto kv_free = [&](int s) { return bar_base + 8 + (2 * SLOTS + s) * 8; };   // BOTH CTAs have finished reading slot s
     auto s_full = [&](int b) { return bar_base + 160 + b * 8; };                // S buffer b holds Q K^T
-    auto p_full = [&](int g, int c) { return bar_base + 184 + (g * 2 + c) * 8; };   // hand-over c of P of warpgroup g's tile is in TMEM
+    // hand-over c of P of the tile in S buffer b is in TMEM.  Per BUFFER, not per warpgroup: with S triple-buffered the
+    // softmax warps can hand over tiles j and j+2 before the MMA issuer has consumed tile j (two phases of a
+    // per-warpgroup barrier -> parity aliasing -> deadlock); tile j+3 cannot be handed over before PV(j) was issued.
+    auto p_full = [&](int b, int c) { return bar_base + 320 + (b * 2 + c) * 8; };
     const uint32_t o_full = bar_base + 216;
     auto pv_done = [&](int g) { return bar_base + 224 + g * 8; };              // PV of warpgroup g's latest tile (and every PV before it) has completed
+    auto m_ready = [&](int g, int quarter) { return bar_base + 256 + (g * 4 + quarter) * 8; };   // warp (g, quarter) has published m
     const uint32_t tmem_slot = bar_base + 240;
     const uint32_t xchg = bar_base + BAR_BYTES;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (1 + SLOTS) * TILE_BYTES + 240);
@@ -99,11 +114,12 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             mbar_init(kv_free(s), 2);
         }
         for (int b = 0; b < SBUF; ++b) mbar_init(s_full(b), 1);
-        for (int g = 0; g < 2; ++g)
-            for (int c = 0; c < 2; ++c) mbar_init(p_full(g, c), SOFTMAX_WARPS / 2);     // one arrival per warp of the warpgroup
+        for (int b = 0; b < SBUF; ++b)
+            for (int c = 0; c < 2; ++c) mbar_init(p_full(b, c), SOFTMAX_WARPS / 2);     // one arrival per warp of the owning warpgroup
         mbar_init(o_full, 1);
         mbar_init(pv_done(0), 1);
         mbar_init(pv_done(1), 1);
+        for (int i = 0; i < 8; ++i) mbar_init(m_ready(i >> 2, i & 3), 1);
         fence_barrier_init();
     }
     if (warp == MMA_WARP) {
@@ -190,6 +206,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 tc_commit(kv_cons(slot));
             }
             int b = 0;                                   // j % 3
+            uint32_t b_round = 0;                        // j / 3
 #pragma unroll 1
             for (int j = 0; j < n_kv; ++j) {
                 if (j + 2 < n_kv) {
@@ -203,17 +220,18 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 }
                 const uint32_t v_addr = next_tile();
                 const int v_slot = slot;
-                // per-warpgroup barriers: the two warpgroups run independently and may hand over out of order
-                mbar_wait(p_full(j & 1, 0), (j >> 1) & 1, 0x220);
+                mbar_wait(p_full(b, 0), b_round & 1, 0x220);
                 tc_fence_after();
                 issue_pv(b, v_addr, j > 0, 0);
-                mbar_wait(p_full(j & 1, 1), (j >> 1) & 1, 0x221);
-                tc_fence_after();
-                issue_pv(b, v_addr, true, 1);
+                if (HO0_GROUPS < BKV / GC) {
+                    mbar_wait(p_full(b, 1), b_round & 1, 0x221);
+                    tc_fence_after();
+                    issue_pv(b, v_addr, true, 1);
+                }
                 tc_commit(kv_cons(v_slot));
                 tc_commit(pv_done(j & 1));
                 if (j + 1 == n_kv) tc_commit(o_full);
-                b = b == 2 ? 0 : b + 1;
+                if (b == 2) { b = 0; ++b_round; } else ++b;
             }
         }
     } else {
@@ -233,9 +251,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const float sl2 = p.scale_log2;
         const uint64_t sl2_2 = f2_pack(sl2, sl2);
         const int tail_valid = p.sk - (n_kv - 1) * BKV;              // valid keys in the last KV tile (1..128)
-        const uint32_t bar_mine = 1 + g * 4 + quarter;               // I arrive here once I have decided m for my tile
-        const uint32_t bar_other = 1 + (1 - g) * 4 + quarter;        // ... and wait here for the decision of the tile before
-        const uint32_t bar_pair = 9 + quarter;                       // both threads of the row (epilogue)
+        const uint32_t bar_pair = 1 + quarter;                       // named barrier of the two threads of the row (epilogue)
         const uint32_t m_addr = xchg + r * 4;
         const uint32_t l_addr = xchg + (BQ + g * BQ + r) * 4, l_other_addr = xchg + (BQ + (1 - g) * BQ + r) * 4;
         float m_last = -INFINITY;     // the reference my l is expressed in
@@ -243,53 +259,75 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
         int b = g;                    // j % 3 of my current tile
         uint32_t b_round = 0;         // j / 3
+#ifdef WVD_ATTN_PROF
+        const bool prof = p.prof != nullptr && blockIdx.x == 2 && blockIdx.y == 0 && lane == 0;
+        uint32_t pc_wait = 0, pc_ld = 0, pc_max = 0, pc_sync = 0, pc_dec = 0, pc_exp = 0, pc_steps = 0, pt = 0;
+#endif
 #pragma unroll 1
         for (int j = g; j < n_kv; j += 2) {
             const uint32_t s_tmem = tmem_base + b * 128 + lane_sel;        // S buffer of tile j; P aliases its columns [0,64)
+#ifdef WVD_ATTN_PROF
+            if (prof) { asm volatile("mov.u32 %0, %%clock;" : "=r"(pt)); ++pc_steps; }
+#endif
             mbar_wait(s_full(b), b_round & 1, 0x300 + b);
             tc_fence_after();
+            PROF_LAP(pc_wait);
             uint32_t s[BKV];
             tmem_ld_32x32b_x32(s_tmem + 0, s + 0);
             tmem_ld_32x32b_x32(s_tmem + 32, s + 32);
             tmem_ld_32x32b_x32(s_tmem + 64, s + 64);
             tmem_ld_32x32b_x32(s_tmem + 96, s + 96);
             tc_wait_ld();
+            PROF_LAP(pc_ld);
             if (j == n_kv - 1 && tail_valid < BKV) {
 #pragma unroll
                 for (int c = 0; c < BKV; ++c)
                     if (c >= tail_valid) s[c] = 0xff800000u;   // -inf
             }
             const float mx = row_max<BKV, 0, BKV>(s, -INFINITY);     // exact row maximum of this tile
+#ifdef WVD_ATTN_PROF
+            if (prof) { uint32_t t_; asm volatile("mov.u32 %0, %%clock;" : "=r"(t_)); t_ += __float_as_uint(mx) & 0u; pc_max += t_ - pt; pt = t_; }
+#endif
             float m_prev = -INFINITY;
             if (j > 0) {
-                named_bar_sync(bar_other, 64);                        // the thread of tile j-1 has published its m
+                // the thread of tile j-1 (other warpgroup, same lane quarter) has published its m; its barrier completes
+                // once per tile of that warpgroup and cannot run ahead: its next tile needs MY decision first
+                mbar_wait(m_ready(1 - g, quarter), ((j - 1) >> 1) & 1, 0x330 + quarter);
                 m_prev = __uint_as_float(ld_shared_volatile_u32(m_addr));
             }
+#ifdef WVD_ATTN_PROF
+            if (prof) { uint32_t t_; asm volatile("mov.u32 %0, %%clock;" : "=r"(t_)); t_ += __float_as_uint(m_prev) & 0u; pc_sync += t_ - pt; pt = t_; }
+#endif
             const float m_new = ((mx - m_prev) * sl2 > REF_MARGIN) ? mx : m_prev;     // tile 0: m_prev = -inf -> mx
             st_shared_u32(m_addr, __float_as_uint(m_new));
-            if (j + 1 < n_kv) named_bar_arrive(bar_mine, 64);
-            if (j > 0 && __any_sync(0xffffffffu, m_new != m_prev)) {
-                // O holds tiles < j relative to m_prev and PV(j-1) may still be accumulating: wait for it, rescale my
-                // row.  Nobody else touches O meanwhile: PV(j) needs my P, and the thread of tile j+1 can only rescale
-                // after PV(j).
-                // PV(j-1) belongs to the OTHER warpgroup's barrier, which can only be one phase away from what I expect:
-                // its previous tile j-3 completed before S(j) did, its next tile j+1 needs PV(j), which needs my P.
-                mbar_wait(pv_done(1 - g), ((j - 1) >> 1) & 1, 0x320);
-                tc_fence_after();
-                const float alpha = fast_exp2((m_prev - m_new) * sl2);       // 1 for the rows that did not move
+            __syncwarp();
+            if (lane == 0 && j + 1 < n_kv) mbar_arrive(m_ready(g, quarter));
+            // Rare path (warp-uniform): some row of this warp moves its reference, or my l is in an older reference.
+            if (__any_sync(0xffffffffu, m_new != m_prev || m_new != m_last)) {
+                if (j > 0 && __any_sync(0xffffffffu, m_new != m_prev)) {
+                    // O holds tiles < j relative to m_prev and PV(j-1) may still be accumulating: wait for it, rescale
+                    // my row.  Nobody else touches O meanwhile: PV(j) needs my P, and the thread of tile j+1 can only
+                    // rescale after PV(j).  PV(j-1) belongs to the OTHER warpgroup's barrier, which can only be one
+                    // phase away from what I expect: its previous tile j-3 completed before S(j) did, its next tile
+                    // j+1 needs PV(j).
+                    mbar_wait(pv_done(1 - g), ((j - 1) >> 1) & 1, 0x320);
+                    tc_fence_after();
+                    const float alpha = fast_exp2((m_prev - m_new) * sl2);       // 1 for the rows that did not move
 #pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
-                    uint32_t o[16];
-                    tmem_ld_32x32b_x16(o_tmem + c * 16, o);
-                    tc_wait_ld();
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t o[16];
+                        tmem_ld_32x32b_x16(o_tmem + c * 16, o);
+                        tc_wait_ld();
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-                    tmem_st_32x32b_x16(o_tmem + c * 16, o);
+                        for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                        tmem_st_32x32b_x16(o_tmem + c * 16, o);
+                    }
+                    tc_wait_st();
                 }
-                tc_wait_st();
+                l *= fast_exp2((m_last - m_new) * sl2);       // 1 if unchanged; first own tile: l = 0, exp2(-inf) = 0
             }
-            if (m_new != m_last) l *= fast_exp2((m_last - m_new) * sl2);      // first own tile: l = 0, exp2(-inf) = 0
             m_last = m_new;
+            PROF_LAP(pc_dec);
             const float neg_m = -m_new * sl2;
             const uint64_t negm_2 = f2_pack(neg_m, neg_m);
             float lsum = 0.f;
@@ -311,13 +349,20 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(p_full(g, q8 == BKV / GC - 1 ? 1 : 0));
+                    if (lane == 0) mbar_arrive(p_full(b, q8 == HO0_GROUPS - 1 ? 0 : 1));
                 }
             }
             l += lsum;
+            PROF_LAP(pc_exp);
             b += 2;
             if (b >= SBUF) { b -= SBUF; ++b_round; }
         }
+#ifdef WVD_ATTN_PROF
+        if (prof) {
+            unsigned long long* o = p.prof + warp * 8;
+            o[0] = pc_wait; o[1] = pc_ld; o[2] = pc_max; o[3] = pc_sync; o[4] = pc_dec; o[5] = pc_exp; o[6] = pc_steps;
+        }
+#endif
 
         // ------------------------------ epilogue: O / l -> global ------------------------------
         named_bar_sync(bar_pair, 64);                                // both threads of the row are past their last tile
@@ -396,6 +441,7 @@ int attention_pair_launch(const void* q, int64_t ldq, const void* k, int64_t ldk
     p.sk = (int)sk;
     p.n_kv = (int)((sk + BKV - 1) / BKV);
     p.scale_log2 = scale * 1.4426950408889634f;
+    p.prof = attn::g_prof_buffer;
     static bool configured = false;
     if (!configured) {
         WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

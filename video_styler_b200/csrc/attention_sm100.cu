@@ -61,6 +61,9 @@ constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 128, 0, 1);   // A = P (TMEM)
 #ifndef WVD_ATTN_RELEASE_GROUP
 #define WVD_ATTN_RELEASE_GROUP 3
 #endif
+#ifndef WVD_ATTN_KERNEL_DEFAULT
+#define WVD_ATTN_KERNEL_DEFAULT 1        // 1 = the two-tile kernel of this file, 2 = the CTA-pair kernel (attention_pair_sm100.cu)
+#endif
 #ifndef WVD_ATTN_TURNS
 #define WVD_ATTN_TURNS 0
 #endif
@@ -491,7 +494,7 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
     static int which = -1;
     if (which < 0) {
         const char* e = getenv("WVD_ATTN_KERNEL");     // developer A/B: 2 = experimental CTA-pair kernel (attention_pair_sm100.cu)
-        which = e ? atoi(e) : 0;
+        which = e ? atoi(e) : WVD_ATTN_KERNEL_DEFAULT;
     }
     // The CTA-pair kernel (one Q tile per CTA, triple-buffered S, K/V multicast across a 2-CTA cluster) measures the
     // same 14.1-14.3 ms as this kernel at c3 and still has a rare deadlock (1 in ~100 launches, tools/attn_stress.py),
