@@ -46,6 +46,9 @@ int wvd_debug_flags(unsigned long long out[8]);
  * record per-phase cycle counters of CTA (1,0) into it (softmax warps: wait/ld/max/exp/st; MMA issuer: waits/issue).
  * Pass NULL to disable (default).                                                                              */
 int wvd_debug_attention_profile(unsigned long long* device_buf);
+/* Test hook: which bf16 attention kernel wvd_attention_fwd[_scatter] dispatches to.  0 = by key length (default: the
+ * CTA-pair kernel for Sk >= 2048, the two-tile kernel below), 1 = always two-tile, 2 = always CTA-pair.            */
+int wvd_debug_attention_kernel(int which);
 
 /* ---- K1/K2: LayerNorm (+ AdaLN modulate) ------------------------------------------------------------
  * out = LN(x) * (1 + scale) + shift            (weight == bias == NULL; shift/scale of length dim)

@@ -158,9 +158,17 @@ def _attn_ref(q, k, v, h, dtype=torch.float32):
     return O.attention(q[None].to(dtype), k[None].to(dtype), v[None].to(dtype), h)[0]
 
 
+@pytest.fixture(params=[1, 2], ids=["two_tile_kernel", "cta_pair_kernel"])
+def attn_kernel(request):
+    """Run the test on BOTH bf16 attention kernels (the default dispatch picks by key length)."""
+    _lib.check(_lib.load().wvd_debug_attention_kernel(request.param), "wvd_debug_attention_kernel")
+    yield request.param
+    _lib.check(_lib.load().wvd_debug_attention_kernel(0), "wvd_debug_attention_kernel")
+
+
 @pytest.mark.parametrize("sq,sk,h", [(1, 1, 1), (128, 128, 1), (72, 72, 2), (256, 256, 2), (300, 512, 2), (257, 129, 3),
-                                      (1280, 1280, 12), (1000, 777, 3)])
-def test_attention_matches_oracle(sq, sk, h):
+                                      (1280, 1280, 12), (1000, 777, 3), (640, 2100, 5)])
+def test_attention_matches_oracle(sq, sk, h, attn_kernel):
     g = torch.Generator().manual_seed(sq + sk)
     q, k, v = (torch.randn(s, h * 128, generator=g).bfloat16() for s in (sq, sk, sk))
     out = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), h)
@@ -168,7 +176,25 @@ def test_attention_matches_oracle(sq, sk, h):
     _close(out, _attn_ref(q, k, v, h), 4e-3)            # bf16 P / bf16 output rounding (same points as FA2)
 
 
-def test_attention_reads_fused_qkv_views_and_large_scores():
+def test_attention_repeated_launches_are_bit_identical(attn_kernel):
+    """Warp-specialised pipelines fail as races: the same launch 40 times, with other work in between, must give the
+    same bits every time and never trip the in-kernel watchdog (a parity-aliasing deadlock of the CTA-pair kernel
+    showed up in ~1 of 100 launches before its P hand-over barriers were indexed by S buffer)."""
+    n, h = 8192, 8
+    g = torch.Generator(device=DEV).manual_seed(11)
+    qkv = torch.randn(n, 3 * h * 128, device=DEV, generator=g).bfloat16()
+    d = h * 128
+    junk = torch.empty(160 << 20, dtype=torch.uint8, device=DEV)
+    ref = None
+    for _ in range(40):
+        junk.add_(1)
+        out = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h)
+        ref = out.clone() if ref is None else ref
+        assert torch.equal(out, ref)
+    _no_timeouts()
+
+
+def test_attention_reads_fused_qkv_views_and_large_scores(attn_kernel):
     """q|k|v column slices of one buffer (the engine's layout); large-magnitude scores exercise the lazy rescale."""
     sq, h = 640, 2
     g = torch.Generator().manual_seed(5)
@@ -183,7 +209,7 @@ def test_attention_reads_fused_qkv_views_and_large_scores():
     _close(out, _attn_ref(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h), 6e-3)
 
 
-def test_attention_properties_at_full_c3_length():
+def test_attention_properties_at_full_c3_length(attn_kernel):
     """29,640 tokens (config c3), 2 heads: (i) V = const -> output = const exactly up to bf16; (ii) key/value
     permutation invariance; (iii) a row subset equals SDPA in fp32."""
     n, h = 29640, 2

@@ -24,3 +24,6 @@ for w in range(8):
     o = b[w * 8:(w + 1) * 8]
     it = max(o[6], 1)
     print(f"softmax warp {w} (warpgroup {w // 4}): per own tile: wait_S {o[0]/it:7.1f} ld {o[1]/it:6.1f} rowmax {o[2]/it:6.1f} m-handoff {o[3]/it:6.1f} decide {o[4]/it:6.1f} exp+handover {o[5]/it:7.1f}  total {sum(o[:6])/it:7.1f} over {o[6]} tiles")
+o = b[72:80]
+it = max(o[5], 1)
+print(f"MMA issuer: per tile: wait K {o[0]/it:6.1f}  wait V {o[1]/it:6.1f}  wait P hand-over0 {o[2]/it:7.1f}  hand-over1 {o[3]/it:7.1f}  issue+commit {o[4]/it:6.1f}  total {sum(o[:5])/it:7.1f}")

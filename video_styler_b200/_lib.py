@@ -17,6 +17,7 @@ SIGNATURES = {
     "wvd_sm_arch": [],
     "wvd_debug_flags": [ctypes.POINTER(ctypes.c_ulonglong)],
     "wvd_debug_attention_profile": [c_void_p],
+    "wvd_debug_attention_kernel": [c_int],
     "wvd_ln_modulate": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                         c_float, c_int, c_void_p],
     "wvd_qk_rmsnorm_rope": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,

@@ -11,8 +11,8 @@
 // columns): S_0 [0,128) | S_1 [128,256) | S_2 [256,384) | O [384,512); P(j) aliases S_(j%3)[0,64).
 // One Q tile per SM would double the K/V traffic out of L2 (the binding resource at 148 SMs), so the two CTAs of a
 // 2-CTA cluster (adjacent Q tiles of the same head) SHARE every K/V tile: each loads one half (64 keys) and TMA
-// multicasts it into both CTAs' shared memory.  A slot is reused only when both CTAs have consumed it (remote mbarrier
-// arrive between the two producer threads).
+// multicasts it into both CTAs' shared memory.  A slot is reused only when both CTAs have consumed it: each MMA issuer's
+// tcgen05.commit is multicast to the slot's "free" barrier of BOTH CTAs.
 //   warps 0-3 / 4-7     softmax warpgroups: one query row per thread, warpgroup g owns the KV tiles j = g (mod 2)
 //   warp 8 (1 thread)   TMA producer: Q tile once, then my half of K_j / V_j (multicast to the pair), 4-slot ring
 //   warp 9 (1 thread)   MMA issuer: S_b = Q K_{j+1}^T (SS) issued AHEAD of O += P_j V_j (TS); also owns the TMEM allocation
@@ -80,7 +80,6 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t bar_base = kv_smem + SLOTS * TILE_BYTES;
     const uint32_t q_full = bar_base;
     auto kv_full = [&](int s) { return bar_base + 8 + s * 8; };                 // slot s holds a complete tile (both halves landed)
-    auto kv_cons = [&](int s) { return bar_base + 8 + (SLOTS + s) * 8; };       // MY MMAs have finished reading slot s
     auto kv_free = [&](int s) { return bar_base + 8 + (2 * SLOTS + s) * 8; };   // BOTH CTAs have finished reading slot s
     auto s_full = [&](int b) { return bar_base + 160 + b * 8; };                // S buffer b holds Q K^T
     // hand-over c of P of the tile in S buffer b is in TMEM.  Per BUFFER, not per warpgroup: with S triple-buffered the
@@ -89,7 +88,6 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     auto p_full = [&](int b, int c) { return bar_base + 320 + (b * 2 + c) * 8; };
     const uint32_t o_full = bar_base + 216;
     auto pv_done = [&](int g) { return bar_base + 224 + g * 8; };              // PV of warpgroup g's latest tile (and every PV before it) has completed
-    auto m_ready = [&](int g, int quarter) { return bar_base + 256 + (g * 4 + quarter) * 8; };   // warp (g, quarter) has published m
     const uint32_t tmem_slot = bar_base + 240;
     const uint32_t xchg = bar_base + BAR_BYTES;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (1 + SLOTS) * TILE_BYTES + 240);
@@ -110,7 +108,6 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_init(q_full, 1);
         for (int s = 0; s < SLOTS; ++s) {
             mbar_init(kv_full(s), 1);
-            mbar_init(kv_cons(s), 1);
             mbar_init(kv_free(s), 2);
         }
         for (int b = 0; b < SBUF; ++b) mbar_init(s_full(b), 1);
@@ -119,7 +116,6 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_init(o_full, 1);
         mbar_init(pv_done(0), 1);
         mbar_init(pv_done(1), 1);
-        for (int i = 0; i < 8; ++i) mbar_init(m_ready(i >> 2, i & 3), 1);
         fence_barrier_init();
     }
     if (warp == MMA_WARP) {
@@ -139,17 +135,11 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             tma_load_2d(q_smem, &tmQ, q_full, head * HD, q_row0);
             tma_load_2d(q_smem + HALF_BYTES, &tmQ, q_full, head * HD + 64, q_row0);
             // Tiles in the order the MMA issuer consumes them: K_0, K_1, then (K_{j+2}, V_j) for j = 0 .. n_kv-1.
-            const uint32_t peer = cta_rank ^ 1u;
             int t = 0;
             auto load = [&](const CUtensorMap* tm, int tile) {
                 const int slot = t % SLOTS;
-                if (t >= SLOTS) {
-                    const uint32_t ph = ((t / SLOTS) - 1) & 1;
-                    mbar_wait(kv_cons(slot), ph, 0x100 + slot);            // my MMAs are done with the old tile
-                    mbar_arrive(kv_free(slot));
-                    mbar_arrive_cluster(mapa_shared(kv_free(slot), peer));
-                    mbar_wait(kv_free(slot), ph, 0x110 + slot);            // ... and so are the peer's
-                }
+                if (t >= SLOTS)      // both CTAs' MMAs are done with the old tile (their commits are multicast to both CTAs)
+                    mbar_wait(kv_free(slot), ((t / SLOTS) - 1) & 1, 0x110 + slot);
                 mbar_expect_tx(kv_full(slot), TILE_BYTES);                  // 16 KB from me + 16 KB from the peer
                 const uint32_t dst = kv_smem + slot * TILE_BYTES + cta_rank * (64 * 128);
                 const int row0 = tile * BKV + static_cast<int>(cta_rank) * 64;
@@ -203,36 +193,54 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 tc_fence_after();
                 issue_qk(j0, k_addr);
                 tc_commit(s_full(j0));
-                tc_commit(kv_cons(slot));
+                tc_commit_multicast(kv_free(slot), 0x3);
             }
             int b = 0;                                   // j % 3
             uint32_t b_round = 0;                        // j / 3
+#ifdef WVD_ATTN_PROF
+            const bool prof = p.prof != nullptr && blockIdx.x == 2 && blockIdx.y == 0;
+            uint32_t pc_k = 0, pc_v = 0, pc_p0 = 0, pc_p1 = 0, pc_issue = 0, pt = 0;
+            if (prof) asm volatile("mov.u32 %0, %%clock;" : "=r"(pt));
+#endif
 #pragma unroll 1
             for (int j = 0; j < n_kv; ++j) {
                 if (j + 2 < n_kv) {
                     // QK^T two steps ahead, into the buffer whose P was consumed by PV(j-1) (issued in the last iteration)
                     const int b2 = b == 0 ? 2 : b - 1;   // (j + 2) % 3
                     const uint32_t k_addr = next_tile();
+                    PROF_LAP(pc_k);
                     tc_fence_after();
                     issue_qk(b2, k_addr);
                     tc_commit(s_full(b2));
-                    tc_commit(kv_cons(slot));
+                    tc_commit_multicast(kv_free(slot), 0x3);
+                    PROF_LAP(pc_issue);
                 }
                 const uint32_t v_addr = next_tile();
                 const int v_slot = slot;
+                PROF_LAP(pc_v);
                 mbar_wait(p_full(b, 0), b_round & 1, 0x220);
+                PROF_LAP(pc_p0);
                 tc_fence_after();
                 issue_pv(b, v_addr, j > 0, 0);
+                PROF_LAP(pc_issue);
                 if (HO0_GROUPS < BKV / GC) {
                     mbar_wait(p_full(b, 1), b_round & 1, 0x221);
+                    PROF_LAP(pc_p1);
                     tc_fence_after();
                     issue_pv(b, v_addr, true, 1);
+                    PROF_LAP(pc_issue);
                 }
-                tc_commit(kv_cons(v_slot));
+                tc_commit_multicast(kv_free(v_slot), 0x3);
                 tc_commit(pv_done(j & 1));
                 if (j + 1 == n_kv) tc_commit(o_full);
                 if (b == 2) { b = 0; ++b_round; } else ++b;
             }
+#ifdef WVD_ATTN_PROF
+            if (prof) {
+                unsigned long long* o = p.prof + MMA_WARP * 8;
+                o[0] = pc_k; o[1] = pc_v; o[2] = pc_p0; o[3] = pc_p1; o[4] = pc_issue; o[5] = n_kv;
+            }
+#endif
         }
     } else {
         // ------------------------------ softmax warps ------------------------------
@@ -251,7 +259,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const float sl2 = p.scale_log2;
         const uint64_t sl2_2 = f2_pack(sl2, sl2);
         const int tail_valid = p.sk - (n_kv - 1) * BKV;              // valid keys in the last KV tile (1..128)
-        const uint32_t bar_pair = 1 + quarter;                       // named barrier of the two threads of the row (epilogue)
+        const uint32_t bar_mine = 1 + g * 4 + quarter;               // I arrive here once I have published m for my tile
+        const uint32_t bar_other = 1 + (1 - g) * 4 + quarter;        // ... and wait here for the m of the tile before
+        const uint32_t bar_pair = 9 + quarter;                       // both threads of the row (epilogue)
         const uint32_t m_addr = xchg + r * 4;
         const uint32_t l_addr = xchg + (BQ + g * BQ + r) * 4, l_other_addr = xchg + (BQ + (1 - g) * BQ + r) * 4;
         float m_last = -INFINITY;     // the reference my l is expressed in
@@ -290,9 +300,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #endif
             float m_prev = -INFINITY;
             if (j > 0) {
-                // the thread of tile j-1 (other warpgroup, same lane quarter) has published its m; its barrier completes
-                // once per tile of that warpgroup and cannot run ahead: its next tile needs MY decision first
-                mbar_wait(m_ready(1 - g, quarter), ((j - 1) >> 1) & 1, 0x330 + quarter);
+                // The thread of tile j-1 (other warpgroup, same scheduler) has published its m: producer / consumer
+                // named barrier (bar.arrive by the publisher, bar.sync here).  It cannot be signalled twice before I
+                // consume it: the publisher's next tile needs MY decision first.
+                named_bar_sync(bar_other, 64);
                 m_prev = __uint_as_float(ld_shared_volatile_u32(m_addr));
             }
 #ifdef WVD_ATTN_PROF
@@ -300,10 +311,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #endif
             const float m_new = ((mx - m_prev) * sl2 > REF_MARGIN) ? mx : m_prev;     // tile 0: m_prev = -inf -> mx
             st_shared_u32(m_addr, __float_as_uint(m_new));
-            __syncwarp();
-            if (lane == 0 && j + 1 < n_kv) mbar_arrive(m_ready(g, quarter));
-            // Rare path (warp-uniform): some row of this warp moves its reference, or my l is in an older reference.
-            if (__any_sync(0xffffffffu, m_new != m_prev || m_new != m_last)) {
+            if (j + 1 < n_kv) named_bar_arrive(bar_mine, 64);
+            // Rare path (warp-uniform): some row of this warp moves its reference, or my l is in an older reference
+            // (m_last <= m_prev <= m_new, so one comparison covers both).
+            if (__any_sync(0xffffffffu, m_new != m_last)) {
                 if (j > 0 && __any_sync(0xffffffffu, m_new != m_prev)) {
                     // O holds tiles < j relative to m_prev and PV(j-1) may still be accumulating: wait for it, rescale
                     // my row.  Nobody else touches O meanwhile: PV(j) needs my P, and the thread of tile j+1 can only

@@ -62,7 +62,7 @@ constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 128, 0, 1);   // A = P (TMEM)
 #define WVD_ATTN_RELEASE_GROUP 3
 #endif
 #ifndef WVD_ATTN_KERNEL_DEFAULT
-#define WVD_ATTN_KERNEL_DEFAULT 1        // 1 = the two-tile kernel of this file, 2 = the CTA-pair kernel (attention_pair_sm100.cu)
+#define WVD_ATTN_KERNEL_DEFAULT 0        // 0 = by key length, 1 = the two-tile kernel of this file, 2 = the CTA-pair kernel (attention_pair_sm100.cu)
 #endif
 #ifndef WVD_ATTN_TURNS
 #define WVD_ATTN_TURNS 0
@@ -421,6 +421,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 unsigned long long* g_prof_buffer = nullptr;
+int g_kernel_select = -1;      // -1 = not yet read from WVD_ATTN_KERNEL; see wvd_debug_attention_kernel
 }  // namespace attn
 
 int attn_read_diag(unsigned long long* out) {
@@ -431,6 +432,12 @@ int attn_read_diag(unsigned long long* out) {
 }
 
 }  // namespace wvd
+
+extern "C" __attribute__((visibility("default"))) int wvd_debug_attention_kernel(int which) {
+    WVD_REQUIRE(which >= 0 && which <= 2, "wvd_debug_attention_kernel: 0 = by key length, 1 = two-tile, 2 = CTA-pair");
+    wvd::attn::g_kernel_select = which;
+    return WVD_OK;
+}
 
 extern "C" __attribute__((visibility("default"))) int wvd_debug_attention_profile(unsigned long long* device_buf) {
     wvd::attn::g_prof_buffer = device_buf;
@@ -491,15 +498,16 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
         WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     }
     cudaStream_t st = (cudaStream_t)stream;
-    static int which = -1;
-    if (which < 0) {
-        const char* e = getenv("WVD_ATTN_KERNEL");     // developer A/B: 2 = experimental CTA-pair kernel (attention_pair_sm100.cu)
-        which = e ? atoi(e) : WVD_ATTN_KERNEL_DEFAULT;
+    if (g_kernel_select < 0) {
+        const char* e = getenv("WVD_ATTN_KERNEL");     // developer A/B: force kernel 1 or 2
+        g_kernel_select = e ? atoi(e) : WVD_ATTN_KERNEL_DEFAULT;
     }
-    // The CTA-pair kernel (one Q tile per CTA, triple-buffered S, K/V multicast across a 2-CTA cluster) measures the
-    // same 14.1-14.3 ms as this kernel at c3 and still has a rare deadlock (1 in ~100 launches, tools/attn_stress.py),
-    // so it is opt-in only.
-    if (which == 2)
+    const int which = g_kernel_select;
+    // Long key sequences (self-attention) go to the CTA-pair kernel (attention_pair_sm100.cu: one Q tile per CTA,
+    // triple-buffered S, K/V multicast across a 2-CTA cluster): 1-2 % faster than this kernel in sustained runs and
+    // 2.4 % faster per launch inside the c3 step.  Short ones (the 512-token text cross-attention: 4 KV steps,
+    // prologue-dominated, 0.49 vs 0.73 ms) stay on the two-tile kernel of this file.
+    if (which == 2 || (which == 0 && sk >= 2048))
         return attention_pair_launch(q, ldq, k, ldk, v, ldv, out, out_peers ? (void* const*)p.out_peer : nullptr, world,
                                      rows_per_peer, ldo, num_heads, sq, sk, scale, emu, st);
     dim3 grid((unsigned)((sq + QT * BQ - 1) / (QT * BQ)), (unsigned)num_heads);
