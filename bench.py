@@ -35,7 +35,7 @@ METRIC = "wan_vace_14b_dit_s_per_denoise_step_832x480x73"
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE self-attention launch at c3, from the committed
     `ncu --set full` capture summary (profiles/, written by tools/ncu_summary.py).  None if the summary is absent."""
-    p = os.path.join(ROOT, "profiles", "r1_attention_c3_v2.txt")
+    p = os.path.join(ROOT, "profiles", "r1_attention_pair_c3.txt")
     if not os.path.exists(p):
         return None
     tot, mult = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -281,11 +281,11 @@ def main():
                              d2h_bytes_per_step=out_host.numel() * 2),
                     gpu_launches=launches, host_enqueue_ms_per_step=host_ms[0],
                     clocks=clocks,
-                    roofline=dict(bound="tensor", kernel="wvd::attn::attention_fwd_kernel (self-attention)",
+                    roofline=dict(bound="tensor", kernel="wvd::attn2::attention_pair_kernel (self-attention)",
                                   achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s",
                                   frac=(achieved / pk["bf16_sustained"]) if achieved else None,
                                   traffic=ncu_traffic_bytes() if args.workload == "c3" and world == 1 else None,
-                                  traffic_unit="bytes per launch (dram read + write, ncu --set full, profiles/r1_attention_c3_v2.txt); "
+                                  traffic_unit="bytes per launch (dram read + write, ncu --set full, profiles/r1_attention_pair_c3.txt); "
                                                "algorithmic minimum 4*A = 1.214e9 (q, k, v read + out written once)",
                                   peak_source=f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
                                   launches_timed=len(att), avg_launch_ms=att_ms,
