@@ -222,16 +222,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    host_ms = []
-
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        h0 = time.perf_counter()
         for _ in range(k):
             fn()
-        host_ms.append((time.perf_counter() - h0) * 1e3 / k)       # host time to ENQUEUE one step (no sync inside)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -279,7 +275,7 @@ def main():
                     tc_frac_of_measured_burst=full_flops / (ms / 1e3) / 1e12 / world / pk["bf16_burst"],
                     e2e=dict(value=ms_e2e / 1e3, unit="s", h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=out_host.numel() * 2),
-                    gpu_launches=launches, host_enqueue_ms_per_step=host_ms[0],
+                    gpu_launches=launches,
                     clocks=clocks,
                     roofline=dict(bound="tensor", kernel="wvd::attn2::attention_pair_kernel (self-attention)",
                                   achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s",
