@@ -209,10 +209,11 @@ def test_attention_reads_fused_qkv_views_and_large_scores(attn_kernel):
     _close(out, _attn_ref(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h), 6e-3)
 
 
-def test_attention_properties_at_full_c3_length(attn_kernel):
-    """29,640 tokens (config c3), 2 heads: (i) V = const -> output = const exactly up to bf16; (ii) key/value
-    permutation invariance; (iii) a row subset equals SDPA in fp32."""
-    n, h = 29640, 2
+@pytest.mark.parametrize("n", [29640, 75600])
+def test_attention_properties_at_full_length(attn_kernel, n):
+    """29,640 tokens (config c3) and 75,600 (config c5), 2 heads: (i) V = const -> output = const exactly up to bf16;
+    (ii) key/value permutation invariance; (iii) a row subset equals SDPA in fp32."""
+    h = 2
     g = torch.Generator(device=DEV).manual_seed(2)
     q = torch.randn(n, h * 128, device=DEV, generator=g).bfloat16()
     k = torch.randn(n, h * 128, device=DEV, generator=g).bfloat16()
@@ -254,12 +255,12 @@ def test_ulysses_layout_kernels():
     assert torch.equal(ops.ulysses_unpack_out(recv.to(DEV), heads, world).cpu(), cpu_backend.ulysses_unpack_out(recv, heads, world))
 
 
-def test_ulysses_peer_scatter_kernels_match_the_collective_layouts():
+@pytest.mark.parametrize("world,heads,n_loc,pad", [(2, 4, 37, 4), (2, 4, 1100, 3), (4, 8, 600, 0)])
+def test_ulysses_peer_scatter_kernels_match_the_collective_layouts(world, heads, n_loc, pad):
     """The fused exchange (peer stores) against the pack / unpack layouts, with the 'peers' being local buffers: what
     rank r scatters must land where pack + all_to_all would have put it, and attention_scatter must leave every query
     row where attention + all_to_all + unpack would have (ragged token count included)."""
     from tests import cpu_backend
-    world, heads, n_loc = 2, 4, 37
     hl, w = heads // world, (heads // world) * 128
     g = torch.Generator().manual_seed(5)
     qkv = [torch.randn(n_loc, 3 * heads * 128, generator=g).bfloat16() for _ in range(world)]
@@ -271,8 +272,9 @@ def test_ulysses_peer_scatter_kernels_match_the_collective_layouts():
     for d in range(world):
         want = torch.stack([packed[src][d] for src in range(world)]).reshape(world * n_loc, 3 * w)   # all_to_all_single
         assert torch.equal(recv[d].cpu(), want)
-    # return trip: 70 real tokens (the last shard is padded by 4 rows), every rank attends its heads over all tokens
-    n = world * n_loc - 4
+    # return trip: the last shard is padded by `pad` rows; every rank attends its heads over all real tokens (the
+    # 2,197- and 2,400-token cases take the long-sequence CTA-pair kernel's scatter epilogue)
+    n = world * n_loc - pad
     outs = [torch.zeros(n_loc, heads * 128, dtype=torch.bfloat16, device=DEV) for _ in range(world)]
     for r in range(world):
         rv = recv[r]
