@@ -104,6 +104,13 @@ int get_tensor_map_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64
     return WVD_OK;
 }
 
+bool first_use_on_current_device(unsigned long long* flag_word) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;      // unknown: configure again (idempotent)
+    const unsigned long long bit = 1ull << dev;
+    return (__atomic_fetch_or(flag_word, bit, __ATOMIC_ACQ_REL) & bit) == 0;
+}
+
 int gemm_read_diag(unsigned long long* out);
 int attn_read_diag(unsigned long long* out);
 int attn_pair_read_diag(unsigned long long* out);

@@ -453,11 +453,10 @@ int attention_pair_launch(const void* q, int64_t ldq, const void* k, int64_t ldk
     p.n_kv = (int)((sk + BKV - 1) / BKV);
     p.scale_log2 = scale * 1.4426950408889634f;
     p.prof = attn::g_prof_buffer;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (first_use_on_current_device(&configured)) {
         WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
     }
     unsigned q_tiles = (unsigned)((sq + BQ - 1) / BQ);
     q_tiles = (q_tiles + 1u) & ~1u;          // whole CTA pairs; a surplus CTA computes rows >= sq and stores nothing

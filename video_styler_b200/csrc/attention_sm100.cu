@@ -492,6 +492,9 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
         const char* e = getenv("WVD_ATTN_EMU");        // tuning knob: 0..3 of every 4 column pairs on the FMA pipes
         int ev = e ? atoi(e) : 0;          // measured on B200: 0 is fastest (the softmax is issue-bound, not MUFU-bound)
         emu = ev < 0 ? 0 : (ev > 3 ? 3 : ev);
+    }
+    static unsigned long long configured = 0;
+    if (first_use_on_current_device(&configured)) {
         WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -133,6 +133,35 @@ ln_modulate_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__
     const float rstd = rsqrtf(warp_sum(s2) / dim + eps);
     keep_packed(raw);
     T* orow = out + row * ldo;
+    if constexpr (MODULATE && !AFFINE && sizeof(T) == 2) {
+        // bf16 fast path of modulate(LN(x), shift, scale): the reference evaluates x * (1 + scale) + shift in bf16, one
+        // rounding per operation (wan_video_dit.py:64-65) -- exactly what the packed bf16x2 instructions do (HADD2 /
+        // HMUL2 round to nearest even once), so the whole tail runs on 2 elements per instruction instead of
+        // emulating each rounding in fp32.  LN output: (x - mean) * rstd in fp32, rounded to bf16 by the pack.
+        const __nv_bfloat162 one2 = __floats2bfloat162_rn(1.0f, 1.0f);
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int vi = lane + 32 * i;
+            if (vi < nvec) {
+                float f[VE];
+                IO::unpack(raw[i], f);
+                const uint4 sc4 = __ldg(reinterpret_cast<const uint4*>(scale + vi * VE));
+                const uint4 sh4 = __ldg(reinterpret_cast<const uint4*>(shift + vi * VE));
+                const uint32_t scw[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, shw[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat162 ln = __floats2bfloat162_rn((f[2 * q] - mean) * rstd, (f[2 * q + 1] - mean) * rstd);
+                    const __nv_bfloat162 sc2 = *reinterpret_cast<const __nv_bfloat162*>(&scw[q]);
+                    const __nv_bfloat162 sh2 = *reinterpret_cast<const __nv_bfloat162*>(&shw[q]);
+                    const __nv_bfloat162 r = __hadd2_rn(__hmul2_rn(ln, __hadd2_rn(one2, sc2)), sh2);   // _rn: never contracted into an FMA
+                    ow[q] = *reinterpret_cast<const uint32_t*>(&r);
+                }
+                *reinterpret_cast<uint4*>(orow + vi * VE) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         const int vi = lane + 32 * i;

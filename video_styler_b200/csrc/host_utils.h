@@ -39,4 +39,8 @@ int get_tensor_map_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64
 
 int sm_count();
 
+// One-time per-DEVICE setup (cudaFuncSetAttribute is per device; a process may drive several GPUs): returns true the
+// first time it is called with this flag word on the current device.  Thread-safe.
+bool first_use_on_current_device(unsigned long long* flag_word);
+
 }  // namespace wvd
