@@ -245,12 +245,28 @@ __device__ __forceinline__ void rms_rope_row(const T* __restrict__ xr, const T* 
     for (int i = 0; i < MAXV; ++i) {
         const int vi = lane + 32 * i;
         if (vi < nvec) {
-            float ww[VE], o[VE], f[VE];
+            float o[VE], f[VE];
             IO::unpack(raw[i], f);
-            IO::load(w + vi * VE, ww);
+            if constexpr (sizeof(T) == 2) {
+                // bf16: norm(x.float()).to(dtype) * weight (wan_video_dit.py:109-111) = one pack (rounds the norm) and
+                // one packed bf16x2 multiply (rounds the product) per two elements -- the reference's rounding points
+                const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(w + vi * VE));
+                const uint32_t wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-            for (int e = 0; e < VE; ++e)   // norm(x.float()).to(dtype) * weight  (wan_video_dit.py:109-111)
-                o[e] = IO::rnd(IO::rnd(f[e] * rstd) * ww[e]);
+                for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat162 n2 = __floats2bfloat162_rn(f[2 * q] * rstd, f[2 * q + 1] * rstd);
+                    const __nv_bfloat162 m2 = __hmul2_rn(n2, *reinterpret_cast<const __nv_bfloat162*>(&wv[q]));
+                    const float2 mf = __bfloat1622float2(m2);
+                    o[2 * q] = mf.x;
+                    o[2 * q + 1] = mf.y;
+                }
+            } else {
+                float ww[VE];
+                IO::load(w + vi * VE, ww);
+#pragma unroll
+                for (int e = 0; e < VE; ++e)   // norm(x.float()).to(dtype) * weight  (wan_video_dit.py:109-111)
+                    o[e] = IO::rnd(IO::rnd(f[e] * rstd) * ww[e]);
+            }
             if (ROPE) {
 #pragma unroll
                 for (int pr = 0; pr < VE / 2; ++pr) {   // (re, im) * (cos + i sin)  (wan_video_dit.py:92-97)
