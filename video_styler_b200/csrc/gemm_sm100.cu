@@ -57,43 +57,51 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     return 0.5f * x * (1.0f + t);
 }
 
+// Epilogue of 8 consecutive columns of one accumulator row, with the reference's rounding points: F.linear rounds
+// acc + bias to bf16 once; GELU-tanh is evaluated in fp32 on that bf16 value and rounded once; GateModule's
+// x + gate * y (wan_video_dit.py:189-194) and the plain residual add round after each operation.  The bf16 operations
+// run as packed bf16x2 instructions (__hmul2_rn / __hadd2_rn: one rounding each, never contracted), two elements per
+// instruction, instead of emulating every rounding in fp32.
 template <int EPI>
 __device__ __forceinline__ void epilogue_store8(const Params& p, const uint32_t* acc, long long row, int col) {
     // acc: 8 fp32 accumulator values (as bits) for columns col..col+7 of `row`
-    float y[8];
+    __nv_bfloat162 y[4];
     if (p.bias != nullptr) {
         const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
-        const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
-        const float bb[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
+        const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = bf16_round(__uint_as_float(acc[i]) + bb[i]);
+        for (int q = 0; q < 4; ++q) {
+            const float2 bf = unpack_bf16x2(bw[q]);
+            y[q] = __floats2bfloat162_rn(__uint_as_float(acc[2 * q]) + bf.x, __uint_as_float(acc[2 * q + 1]) + bf.y);
+        }
     } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = bf16_round(__uint_as_float(acc[i]));
+        for (int q = 0; q < 4; ++q) y[q] = __floats2bfloat162_rn(__uint_as_float(acc[2 * q]), __uint_as_float(acc[2 * q + 1]));
     }
     if (EPI == WVD_EPI_BIAS_GELU) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = gelu_tanh(y[i]);
+        for (int q = 0; q < 4; ++q) {
+            const float2 yf = __bfloat1622float2(y[q]);
+            y[q] = __floats2bfloat162_rn(gelu_tanh(yf.x), gelu_tanh(yf.y));
+        }
     }
     if (EPI == WVD_EPI_BIAS_GATE_RES) {
         const uint4 g = __ldg(reinterpret_cast<const uint4*>(p.gate + col));
-        const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
-        const float gg[8] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y};
+        const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = bf16_round(gg[i] * y[i]);
+        for (int q = 0; q < 4; ++q) y[q] = __hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&gw[q]), y[q]);
     }
     if (EPI == WVD_EPI_BIAS_RES || EPI == WVD_EPI_BIAS_GATE_RES) {
         const uint4 r = *reinterpret_cast<const uint4*>(p.res + row * p.ldr + col);
-        const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z), r3 = unpack_bf16x2(r.w);
-        const float rr[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
+        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = rr[i] + y[i];
+        for (int q = 0; q < 4; ++q) y[q] = __hadd2_rn(*reinterpret_cast<const __nv_bfloat162*>(&rw[q]), y[q]);
     }
     uint4 o;
-    o.x = pack_bf16x2(y[0], y[1]);
-    o.y = pack_bf16x2(y[2], y[3]);
-    o.z = pack_bf16x2(y[4], y[5]);
-    o.w = pack_bf16x2(y[6], y[7]);
+    o.x = *reinterpret_cast<const uint32_t*>(&y[0]);
+    o.y = *reinterpret_cast<const uint32_t*>(&y[1]);
+    o.z = *reinterpret_cast<const uint32_t*>(&y[2]);
+    o.w = *reinterpret_cast<const uint32_t*>(&y[3]);
     *reinterpret_cast<uint4*>(p.C + row * p.ldc + col) = o;
 }
 
