@@ -40,8 +40,17 @@ constexpr int HO0_GROUPS = WVD_ATTN2_HO0;     // groups of 16 keys in the first 
 constexpr int TILE_BYTES = 128 * 128 * 2;     // 32 KB
 constexpr int HALF_BYTES = TILE_BYTES / 2;    // one 64-column TMA box of 128 rows
 constexpr int SLOTS = 6;                      // K/V ring: 6 x 32 KB + 32 KB of Q = 224 KB of shared memory
+#ifdef WVD_ATTN2_QTMEM
+// Variant: Q resident in TMEM (TS-mode QK^T: only K is read from shared memory, a third less operand traffic) at the
+// price of the third S buffer: S_0 [0,128) | S_1 [128,256) | O [256,384) | Q [384,448) (bf16 pairs).
+constexpr int SBUF = 2;
+constexpr bool QTMEM = true;
+#else
 constexpr int SBUF = 3;                       // S buffers in TMEM
+constexpr bool QTMEM = false;
+#endif
 constexpr int O_COL = SBUF * 128;             // first TMEM column of the O accumulator
+constexpr int Q_COL = 384;                    // QTMEM only
 constexpr int SOFTMAX_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9;
 constexpr int NUM_THREADS = 10 * 32;
 constexpr int BAR_BYTES = 384;
@@ -52,6 +61,8 @@ constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 128, 0, 1);   // A = P (TMEM)
 constexpr float REF_MARGIN = 8.0f;
 
 struct Params {
+    const __nv_bfloat16* q;                   // QTMEM variant: the softmax threads read their Q rows from global memory
+    long long ldq;
     __nv_bfloat16* out;
     long long ldo;
     __nv_bfloat16* out_peer[WVD_MAX_PEERS];   // Ulysses return trip fused into the epilogue (see attention_sm100.cu)
@@ -88,6 +99,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     auto p_full = [&](int b, int c) { return bar_base + 320 + (b * 2 + c) * 8; };
     const uint32_t o_full = bar_base + 216;
     auto pv_done = [&](int g) { return bar_base + 224 + g * 8; };              // PV of warpgroup g's latest tile (and every PV before it) has completed
+    const uint32_t q_ready = bar_base + 368;                                     // QTMEM: Q is in TMEM
     const uint32_t tmem_slot = bar_base + 240;
     const uint32_t xchg = bar_base + BAR_BYTES;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (1 + SLOTS) * TILE_BYTES + 240);
@@ -106,6 +118,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     if (warp == MMA_WARP && lane == 0) {
         mbar_init(q_full, 1);
+        mbar_init(q_ready, SOFTMAX_WARPS / 2);
         for (int s = 0; s < SLOTS; ++s) {
             mbar_init(kv_full(s), 1);
             mbar_init(kv_free(s), 2);
@@ -131,9 +144,11 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (warp == TMA_WARP) {
         if (elect_one()) {
             // ------------------------------ TMA producer ------------------------------
-            mbar_expect_tx(q_full, TILE_BYTES);
-            tma_load_2d(q_smem, &tmQ, q_full, head * HD, q_row0);
-            tma_load_2d(q_smem + HALF_BYTES, &tmQ, q_full, head * HD + 64, q_row0);
+            if (!QTMEM) {
+                mbar_expect_tx(q_full, TILE_BYTES);
+                tma_load_2d(q_smem, &tmQ, q_full, head * HD, q_row0);
+                tma_load_2d(q_smem + HALF_BYTES, &tmQ, q_full, head * HD + 64, q_row0);
+            }
             // Tiles in the order the MMA issuer consumes them: K_0, K_1, then (K_{j+2}, V_j) for j = 0 .. n_kv-1.
             int t = 0;
             auto load = [&](const CUtensorMap* tm, int tile) {
@@ -151,8 +166,13 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             if (n_kv > 1) load(&tmK, 1);
 #pragma unroll 1
             for (int j = 0; j < n_kv; ++j) {
-                if (j + 2 < n_kv) load(&tmK, j + 2);
-                load(&tmV, j);
+                if (SBUF == 3) {                 // QK^T(j+2) is issued BEFORE PV(j)
+                    if (j + 2 < n_kv) load(&tmK, j + 2);
+                    load(&tmV, j);
+                } else {                         // two S buffers: QK^T(j+2) reuses the buffer of P(j), after PV(j)
+                    load(&tmV, j);
+                    if (j + 2 < n_kv) load(&tmK, j + 2);
+                }
             }
         }
     } else if (warp == MMA_WARP) {
@@ -163,8 +183,12 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
                 for (int kk = 0; kk < HD / 16; ++kk) {
                     const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
-                    umma_ss(d, make_smem_desc_sw128(q_smem + off, 16, 1024), make_smem_desc_sw128(k_addr + off, 16, 1024),
-                            IDESC_QK, kk != 0 ? 1u : 0u);
+                    if (QTMEM)
+                        umma_ts(d, tmem_base + Q_COL + kk * 8, make_smem_desc_sw128(k_addr + off, 16, 1024), IDESC_QK,
+                                kk != 0 ? 1u : 0u);
+                    else
+                        umma_ss(d, make_smem_desc_sw128(q_smem + off, 16, 1024), make_smem_desc_sw128(k_addr + off, 16, 1024),
+                                IDESC_QK, kk != 0 ? 1u : 0u);
                 }
             };
             // O += P[:, keys of hand-over c] V[keys of hand-over c, :]; hand-over 0 = the first HO0_GROUPS groups of 16 keys
@@ -187,7 +211,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 ++t;
                 return kv_smem + slot * TILE_BYTES;
             };
-            mbar_wait(q_full, 0, 0x210);
+            if (QTMEM) mbar_wait(q_ready, 0, 0x211); else mbar_wait(q_full, 0, 0x210);
+            tc_fence_after();
             for (int j0 = 0; j0 < 2 && j0 < n_kv; ++j0) {
                 const uint32_t k_addr = next_tile();
                 tc_fence_after();
@@ -204,7 +229,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #endif
 #pragma unroll 1
             for (int j = 0; j < n_kv; ++j) {
-                if (j + 2 < n_kv) {
+                if (SBUF == 3 && j + 2 < n_kv) {
                     // QK^T two steps ahead, into the buffer whose P was consumed by PV(j-1) (issued in the last iteration)
                     const int b2 = b == 0 ? 2 : b - 1;   // (j + 2) % 3
                     const uint32_t k_addr = next_tile();
@@ -233,7 +258,15 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 tc_commit_multicast(kv_free(v_slot), 0x3);
                 tc_commit(pv_done(j & 1));
                 if (j + 1 == n_kv) tc_commit(o_full);
-                if (b == 2) { b = 0; ++b_round; } else ++b;
+                if (SBUF == 2 && j + 2 < n_kv) {
+                    // two S buffers: QK^T(j+2) goes into the buffer P(j) has just been read from (in-order tensor pipe)
+                    const uint32_t k_addr = next_tile();
+                    tc_fence_after();
+                    issue_qk(b, k_addr);
+                    tc_commit(s_full(b));
+                    tc_commit_multicast(kv_free(slot), 0x3);
+                }
+                if (++b == SBUF) { b = 0; ++b_round; }
             }
 #ifdef WVD_ATTN_PROF
             if (prof) {
@@ -264,6 +297,22 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const uint32_t bar_pair = 9 + quarter;                       // both threads of the row (epilogue)
         const uint32_t m_addr = xchg + r * 4;
         const uint32_t l_addr = xchg + (BQ + g * BQ + r) * 4, l_other_addr = xchg + (BQ + (1 - g) * BQ + r) * 4;
+        if (QTMEM && g == 0) {
+            // my Q row -> TMEM (A operand of the TS-mode QK^T: lane = row, 32-bit column c = elements 2c, 2c+1)
+            uint32_t qw[64];
+            const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<long long>(row) * p.ldq + head * HD);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const uint4 v = row < p.sq ? __ldg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+                qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
+            }
+            tmem_st_32x32b_x32(tmem_base + Q_COL + lane_sel, qw);
+            tmem_st_32x32b_x32(tmem_base + Q_COL + 32 + lane_sel, qw + 32);
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_ready);
+        }
         float m_last = -INFINITY;     // the reference my l is expressed in
         float l = 0.f;                // sum over MY tiles
 
@@ -294,7 +343,11 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 for (int c = 0; c < BKV; ++c)
                     if (c >= tail_valid) s[c] = 0xff800000u;   // -inf
             }
+#ifdef WVD_ATTN2_EXPERIMENT_PARTIAL_MAX      // timing experiment only (NOT exact): how much does the exact row maximum cost?
+            const float mx = row_max<BKV, 0, 32>(s, -INFINITY);
+#else
             const float mx = row_max<BKV, 0, BKV>(s, -INFINITY);     // exact row maximum of this tile
+#endif
 #ifdef WVD_ATTN_PROF
             if (prof) { uint32_t t_; asm volatile("mov.u32 %0, %%clock;" : "=r"(t_)); t_ += __float_as_uint(mx) & 0u; pc_max += t_ - pt; pt = t_; }
 #endif
@@ -440,6 +493,8 @@ int attention_pair_launch(const void* q, int64_t ldq, const void* k, int64_t ldk
     rc = get_tensor_map_bf16(&tmV, v, (uint64_t)sk, (uint64_t)width, (uint64_t)ldv, BKV / 2);
     if (rc) return rc;
     Params p;
+    p.q = (const __nv_bfloat16*)q;
+    p.ldq = ldq;
     p.out = (__nv_bfloat16*)out;
     p.ldo = ldo;
     p.rows_per_peer = 0;
