@@ -163,7 +163,7 @@ def test_c2_bf16_parity_full_size():
 
 def test_c3_bf16_parity_full_width_reduced_depth():
     """Config c3 shapes (14B width, VACE + merged rank-128 LoRA stand-in, 29,640 tokens) at 6 main layers + 2 VACE
-    blocks so the oracle fits the test budget; the full-depth number is produced by tools/parity_c3.py."""
+    blocks so the oracle fits the test budget; the full-depth number is produced by tools/eager_compare.py --layers 40."""
     m = _big_case("14B", (1, 16, 19, 60, 104), True, layers=6)
     print("c3 (6+2 layers) ours-bf16 vs oracle-bf16:", m)
     assert m["cos"] >= 0.999 and m["rel_l2"] <= 1e-2, m
