@@ -332,10 +332,16 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             tc_fence_after();
             PROF_LAP(pc_wait);
             uint32_t s[BKV];
+#ifdef WVD_ATTN2_EXPERIMENT_NO_LOAD       // timing experiment only (wrong results): what do the S loads from TMEM cost?
+            tmem_ld_32x32b_x32(s_tmem + 0, s + 0);
+#pragma unroll
+            for (int c = 32; c < BKV; ++c) s[c] = s[c & 31] + c;
+#else
             tmem_ld_32x32b_x32(s_tmem + 0, s + 0);
             tmem_ld_32x32b_x32(s_tmem + 32, s + 32);
             tmem_ld_32x32b_x32(s_tmem + 64, s + 64);
             tmem_ld_32x32b_x32(s_tmem + 96, s + 96);
+#endif
             tc_wait_ld();
             PROF_LAP(pc_ld);
             if (j == n_kv - 1 && tail_valid < BKV) {
@@ -408,6 +414,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     case 6: lsum += exp_chunk<BKV, 6 * GC, 7 * GC, EMU_OF_4>(s, pk, sl2_2, negm_2); break;
                     default: lsum += exp_chunk<BKV, 7 * GC, 8 * GC, EMU_OF_4>(s, pk, sl2_2, negm_2); break;
                 }
+#ifdef WVD_ATTN2_EXPERIMENT_NO_STORE      // timing experiment only (wrong results): what do the P stores to TMEM cost?
+                if (q8 == 0 || __float_as_uint(lsum) == 0x12345678u)
+#endif
                 store_p<GC / 2>(s_tmem + q8 * (GC / 2), pk);
                 if (q8 == HO0_GROUPS - 1 || q8 == BKV / GC - 1) {
                     tc_wait_st();
