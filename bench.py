@@ -153,7 +153,7 @@ def run_reference(args, rank):
 
 def exchange_kind():
     from video_styler_b200 import ulysses
-    kinds = {type(e).__name__ for e in ulysses._EXCHANGES.values()}
+    kinds = {("UlyssesExchange" if getattr(e, "_nccl_only", False) else type(e).__name__) for e in ulysses._EXCHANGES.values()}
     return {"P2PUlyssesExchange": "all-to-alls fused into the pack / attention kernels over NVLink peer memory",
             "UlyssesExchange": "NCCL all_to_all_single"}.get(next(iter(kinds), ""), "none")
 

@@ -79,6 +79,7 @@ class P2PUlyssesExchange(UlyssesExchange):
     def __init__(self, group, n_tokens: int):
         super().__init__(group, n_tokens)
         self._bufs = {}
+        self._nccl_only = False
 
     def _buffers(self, n_loc: int, heads: int, device):
         key = (n_loc, heads)
@@ -98,6 +99,30 @@ class P2PUlyssesExchange(UlyssesExchange):
             self._bufs[key] = (recv, aout, h_recv, h_out, [int(x) for x in h_recv.buffer_ptrs], [int(x) for x in h_out.buffer_ptrs])
         return self._bufs[key]
 
+    def _buffers_or_none(self, n_loc: int, heads: int, device):
+        """The symmetric buffers, or None if the rendezvous is not possible on this box (no peer access, symmetric
+        memory unsupported ...).  The verdict is agreed on by all ranks (the rendezvous is a collective), and the
+        exchange then stays on NCCL collectives for good -- still the GPU path, just not the fused one."""
+        if self._nccl_only:
+            return None
+        key = (n_loc, heads)
+        if key in self._bufs:
+            return self._bufs[key]
+        ok = torch.ones(1, device=device, dtype=torch.int32)
+        try:
+            bufs = self._buffers(n_loc, heads, device)
+        except Exception as e:      # noqa: BLE001 -- any failure of the optional fast path selects the baseline
+            bufs = None
+            ok.zero_()
+            import warnings
+            warnings.warn(f"peer-memory Ulysses exchange unavailable ({e!r}); using NCCL all_to_all")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            self._nccl_only = True
+            self._bufs.pop(key, None)
+            return None
+        return bufs
+
     def attend(self, ops, qkv, heads: int, out, ws):
         p, r = self.world, self.rank
         if heads % p != 0:
@@ -105,7 +130,10 @@ class P2PUlyssesExchange(UlyssesExchange):
         n_loc = qkv.shape[0]
         hl = heads // p
         w = hl * 128
-        recv, aout, h_recv, h_out, recv_ptrs, out_ptrs = self._buffers(n_loc, heads, qkv.device)
+        bufs = self._buffers_or_none(n_loc, heads, qkv.device)
+        if bufs is None:
+            return super().attend(ops, qkv, heads, out, ws)
+        recv, aout, h_recv, h_out, recv_ptrs, out_ptrs = bufs
         # (1) q|k|v -> every rank's receive buffer.  Safe to overwrite: every rank passed the previous barrier (2)
         #     only after its previous attention had finished reading.
         ops.ulysses_scatter_qkv(qkv, heads, recv_ptrs, r)
