@@ -49,6 +49,12 @@ constexpr bool QTMEM = true;
 constexpr int SBUF = 3;                       // S buffers in TMEM
 constexpr bool QTMEM = false;
 #endif
+#ifndef WVD_ATTN2_PAIRSLOTS
+#define WVD_ATTN2_PAIRSLOTS 1
+#endif
+// K_{j+2} and V_j share one ring slot and ONE barrier: the MMA issuer's per-tile serial time (mbarrier probes cost
+// ~100-200 cycles each on that single thread) is what bounds the kernel, so it waits once per step for its operands.
+constexpr bool PAIRSLOTS = WVD_ATTN2_PAIRSLOTS != 0 && SBUF == 3;
 constexpr int O_COL = SBUF * 128;             // first TMEM column of the O accumulator
 constexpr int Q_COL = 384;                    // QTMEM only
 constexpr int SOFTMAX_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9;
@@ -149,6 +155,27 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 tma_load_2d(q_smem, &tmQ, q_full, head * HD, q_row0);
                 tma_load_2d(q_smem + HALF_BYTES, &tmQ, q_full, head * HD + 64, q_row0);
             }
+            if (PAIRSLOTS) {
+                // load q = j + 2 carries (K_q, V_{q-2}) into pair slot q % 3 (K at +0, V at +32 KB), one barrier for both
+                for (int q = 0; q <= n_kv + 1; ++q) {
+                    const bool has_k = q < n_kv, has_v = q >= 2;
+                    if (!has_k && !has_v) continue;                          // q = 1 of a single-tile sequence
+                    const int ps = q % 3;
+                    if (q >= 3) mbar_wait(kv_free(ps), ((q / 3) - 1) & 1, 0x110 + ps);   // both CTAs are done with the slot
+                    mbar_expect_tx(kv_full(ps), (has_k ? TILE_BYTES : 0) + (has_v ? TILE_BYTES : 0));
+                    const uint32_t dst = kv_smem + ps * 2 * TILE_BYTES + cta_rank * (64 * 128);
+                    if (has_k) {
+                        const int row0 = q * BKV + static_cast<int>(cta_rank) * 64;
+                        tma_load_2d_multicast(dst, &tmK, kv_full(ps), head * HD, row0, 0x3);
+                        tma_load_2d_multicast(dst + HALF_BYTES, &tmK, kv_full(ps), head * HD + 64, row0, 0x3);
+                    }
+                    if (has_v) {
+                        const int row0 = (q - 2) * BKV + static_cast<int>(cta_rank) * 64;
+                        tma_load_2d_multicast(dst + TILE_BYTES, &tmV, kv_full(ps), head * HD, row0, 0x3);
+                        tma_load_2d_multicast(dst + TILE_BYTES + HALF_BYTES, &tmV, kv_full(ps), head * HD + 64, row0, 0x3);
+                    }
+                }
+            } else {
             // Tiles in the order the MMA issuer consumes them: K_0, K_1, then (K_{j+2}, V_j) for j = 0 .. n_kv-1.
             int t = 0;
             auto load = [&](const CUtensorMap* tm, int tile) {
@@ -174,6 +201,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     if (j + 2 < n_kv) load(&tmK, j + 2);
                 }
             }
+            }   // !PAIRSLOTS
         }
     } else if (warp == MMA_WARP) {
         if (elect_one()) {
@@ -213,6 +241,41 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             };
             if (QTMEM) mbar_wait(q_ready, 0, 0x211); else mbar_wait(q_full, 0, 0x210);
             tc_fence_after();
+            if (PAIRSLOTS) {
+                for (int q = 0; q < 2 && q < n_kv; ++q) {                    // K_0, K_1
+                    mbar_wait(kv_full(q), 0, 0x200 + q);
+                    tc_fence_after();
+                    issue_qk(q, kv_smem + q * 2 * TILE_BYTES);
+                    tc_commit(s_full(q));
+                    tc_commit_multicast(kv_free(q), 0x3);
+                }
+                int b = 0;                                   // j % 3
+                uint32_t b_round = 0;                        // j / 3
+#pragma unroll 1
+                for (int j = 0; j < n_kv; ++j) {
+                    const int q = j + 2, ps = b == 0 ? 2 : b - 1;             // ps = q % 3 = (j + 2) % 3
+                    mbar_wait(kv_full(ps), (q / 3) & 1, 0x200 + ps);         // K_{j+2} and V_j, one probe
+                    tc_fence_after();
+                    const uint32_t base = kv_smem + ps * 2 * TILE_BYTES;
+                    if (j + 2 < n_kv) {
+                        // QK^T two steps ahead, into the buffer whose P was consumed by PV(j-1) (issued in the last iteration)
+                        issue_qk(ps, base);
+                        tc_commit(s_full(ps));
+                    }
+                    mbar_wait(p_full(b, 0), b_round & 1, 0x220);
+                    tc_fence_after();
+                    issue_pv(b, base + TILE_BYTES, j > 0, 0);
+                    if (HO0_GROUPS < BKV / GC) {
+                        mbar_wait(p_full(b, 1), b_round & 1, 0x221);
+                        tc_fence_after();
+                        issue_pv(b, base + TILE_BYTES, true, 1);
+                    }
+                    tc_commit_multicast(kv_free(ps), 0x3);
+                    tc_commit(pv_done(j & 1));
+                    if (j + 1 == n_kv) tc_commit(o_full);
+                    if (++b == SBUF) { b = 0; ++b_round; }
+                }
+            } else {
             for (int j0 = 0; j0 < 2 && j0 < n_kv; ++j0) {
                 const uint32_t k_addr = next_tile();
                 tc_fence_after();
@@ -274,6 +337,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 o[0] = pc_k; o[1] = pc_v; o[2] = pc_p0; o[3] = pc_p1; o[4] = pc_issue; o[5] = n_kv;
             }
 #endif
+            }   // !PAIRSLOTS
         }
     } else {
         // ------------------------------ softmax warps ------------------------------
