@@ -13,9 +13,17 @@
 // 2-CTA cluster (adjacent Q tiles of the same head) SHARE every K/V tile: each loads one half (64 keys) and TMA
 // multicasts it into both CTAs' shared memory.  A slot is reused only when both CTAs have consumed it: each MMA issuer's
 // tcgen05.commit is multicast to the slot's "free" barrier of BOTH CTAs.
+// The single MMA-issuing thread turned out to be the last bound (every mbarrier probe costs it 100-400 cycles): K_{j+2}
+// and V_j therefore travel in ONE ring slot behind ONE barrier, and barriers are indexed by the resource that limits how
+// far a producer can run ahead (P hand-overs by S buffer) -- a barrier that can advance two phases before its consumer
+// waits dead-locks on parity aliasing (tools/attn_stress.py, ~1 in 100 launches before the fix).
 //   warps 0-3 / 4-7     softmax warpgroups: one query row per thread, warpgroup g owns the KV tiles j = g (mod 2)
-//   warp 8 (1 thread)   TMA producer: Q tile once, then my half of K_j / V_j (multicast to the pair), 4-slot ring
-//   warp 9 (1 thread)   MMA issuer: S_b = Q K_{j+1}^T (SS) issued AHEAD of O += P_j V_j (TS); also owns the TMEM allocation
+//   warp 8 (1 thread)   TMA producer: Q tile once, then my 64-key half of (K_{j+2}, V_j) per step, multicast to the
+//                       pair, ring of 3 pair slots (192 KB)
+//   warp 9 (1 thread)   MMA issuer: S_(j+2)%3 = Q K_{j+2}^T (SS) issued AHEAD of O += P_j V_j (TS); owns the TMEM allocation
+// Compile-time variants kept for A/B: WVD_ATTN2_PAIRSLOTS=0 (separate K / V slots and barriers),
+// WVD_ATTN2_QTMEM (Q in TMEM, two S buffers), WVD_ATTN2_HO0 (keys in the first P hand-over / 16), WVD_ATTN2_EXPERIMENT_*
+// (timing experiments that produce WRONG results on purpose).
 #include <math.h>
 #include <stdlib.h>
 
@@ -39,7 +47,7 @@ constexpr int GC = 16;                        // columns per exp2 / store group
 constexpr int HO0_GROUPS = WVD_ATTN2_HO0;     // groups of 16 keys in the first hand-over of P (8 = a single hand-over)
 constexpr int TILE_BYTES = 128 * 128 * 2;     // 32 KB
 constexpr int HALF_BYTES = TILE_BYTES / 2;    // one 64-column TMA box of 128 rows
-constexpr int SLOTS = 6;                      // K/V ring: 6 x 32 KB + 32 KB of Q = 224 KB of shared memory
+constexpr int SLOTS = 6;                      // K/V ring: 6 x 32 KB (= 3 pair slots) + 32 KB of Q = 224 KB of shared memory
 #ifdef WVD_ATTN2_QTMEM
 // Variant: Q resident in TMEM (TS-mode QK^T: only K is read from shared memory, a third less operand traffic) at the
 // price of the third S buffer: S_0 [0,128) | S_1 [128,256) | O [256,384) | Q [384,448) (bf16 pairs).
