@@ -39,16 +39,13 @@ enum {
 const char* wvd_last_error(void);
 int wvd_version(void);          /* 10000*major + 100*minor + patch */
 int wvd_sm_arch(void);          /* 100: the only architecture this library is compiled for (sm_100a) */
-/* Test hook: synchronises the device, copies out and clears the in-kernel watchdog record
- * (out[0] = number of mbarrier waits that timed out, out[1] = tag of the last one, out[2] = block, out[3] = thread). */
+/* Synchronises the device, copies out and clears the in-kernel watchdog record (out[0] = number of mbarrier waits
+ * that timed out, out[1] = tag of the first one, out[2] = block, out[3] = thread).  A timed-out wait also TRAPS the
+ * kernel, so the launch fails with a sticky CUDA error and this call (like every later one) returns WVD_ERR_CUDA.  */
 int wvd_debug_flags(unsigned long long out[8]);
-/* Developer hook: when device_buf (>= 128 uint64 of device memory) is non-NULL, subsequent wvd_attention_fwd launches
- * record per-phase cycle counters of CTA (1,0) into it (softmax warps: wait/ld/max/exp/st; MMA issuer: waits/issue).
- * Pass NULL to disable (default).                                                                              */
-int wvd_debug_attention_profile(unsigned long long* device_buf);
-/* Test hook: which bf16 attention kernel wvd_attention_fwd[_scatter] dispatches to.  0 = by key length (default: the
- * CTA-pair kernel for Sk >= 2048, the two-tile kernel below), 1 = always two-tile, 2 = always CTA-pair.            */
-int wvd_debug_attention_kernel(int which);
+/* Build identity: "wvd <version> sm_100a src=<first 16 hex digits of the sha256 over csrc + include at build time>".
+ * tests/test_abi.py compares it with the hash of the sources in the tree, so a stale prebuilt library is caught.   */
+const char* wvd_build_info(void);
 
 /* ---- K1/K2: LayerNorm (+ AdaLN modulate) ------------------------------------------------------------
  * out = LN(x) * (1 + scale) + shift            (weight == bias == NULL; shift/scale of length dim)
@@ -69,6 +66,11 @@ int wvd_ln_modulate(const void* x, int64_t ldx, const void* shift, const void* s
  * 2 = width (21) -- the reference's complex128 tables (wan_video_dit.py:75-89) cast to fp32.
  * Token n (global index token_offset + local row) sits at (f, h, w) = (n / (gh*gw), (n / gw) % gh, n % gw);
  * frame_ids (int32[gf], may be NULL) replaces f by frame_ids[f] (rope_indices, wan_video_dit.py:378-384).
+ * Rows whose global index lies past the grid are the zero padding of the last Ulysses shard
+ * (wan_video_new.py:1414-1416): they are processed with the last frame's angles and never attended.
+ * Per-token mode: grid_f == grid_h == grid_w == 0 makes rope_cs a (n_tokens, 64) float2 (cos, sin) table indexed by
+ * the local row -- the `freqs` tensor (N, 1, 64) complex that the reference passes to DiTBlock.forward
+ * (wan_video_dit.py:214-230), cast to fp32 pairs.
  * q_out/k_out may alias q/k.  head_dim must be 128.                                                      */
 int wvd_qk_rmsnorm_rope(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* wq, const void* wk,
                         void* q_out, int64_t ldqo, void* k_out, int64_t ldko, int64_t n_tokens, int dim,
@@ -97,6 +99,14 @@ int wvd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
 int wvd_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                       void* out, int64_t ldo, int num_heads, int64_t sq, int64_t sk, int head_dim, float scale,
                       wvd_stream_t stream);
+/* Two kernels sit behind it: WVD_ATTN_TWO_TILE (two Q tiles per CTA; the 512-key text cross-attention) and
+ * WVD_ATTN_PAIR (2-CTA clusters sharing K/V, triple-buffered S in TMEM; long self-attention).  WVD_ATTN_AUTO picks by
+ * key length (PAIR for sk >= 2048) and is what wvd_attention_fwd uses.  The selector is an ARGUMENT -- the library
+ * keeps no mutable dispatch state -- so that the parity tests can run both kernels on the same inputs.            */
+enum { WVD_ATTN_AUTO = 0, WVD_ATTN_TWO_TILE = 1, WVD_ATTN_PAIR = 2 };
+int wvd_attention_fwd_select(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                             void* out, int64_t ldo, int num_heads, int64_t sq, int64_t sk, int head_dim, float scale,
+                             int which, wvd_stream_t stream);
 
 /* ---- fp32 fall-through kernels (fp32 mode of the parity contract; CUDA-core math, not tuned) ----------- */
 int wvd_gemm_f32(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc,
@@ -131,7 +141,8 @@ int wvd_ulysses_scatter_qkv(const void* qkv, int64_t ld, void* const* recv_ptrs,
                             int head_dim, int world, int rank, wvd_stream_t stream);
 int wvd_attention_fwd_scatter(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                               void* const* out_ptrs, int64_t ldo, int64_t rows_per_peer, int64_t col_offset, int world,
-                              int num_heads, int64_t sq, int64_t sk, int head_dim, float scale, wvd_stream_t stream);
+                              int num_heads, int64_t sq, int64_t sk, int head_dim, float scale, int which,
+                              wvd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,11 @@ def make_rope_table(freqs, device):
     return tab
 
 
+def rope_table_from_freqs(freqs, device):
+    f = freqs.reshape(-1, 64)
+    return torch.stack([f.real, f.imag], dim=-1).to(torch.float64)
+
+
 def qk_rmsnorm_rope(q, k, wq, wk, eps, rope_table=None, grid=(1, 1, 1), token_offset=0, frame_ids=None,
                     q_out=None, k_out=None):
     def one(t, w_, dst):
@@ -43,11 +48,14 @@ def qk_rmsnorm_rope(q, k, wq, wk, eps, rope_table=None, grid=(1, 1, 1), token_of
         if rope_table is not None:
             n = t.shape[0]
             gf, gh, gw = grid
-            idx = torch.arange(n) + token_offset
-            pf, ph, pw = idx // (gh * gw), (idx // gw) % gh, idx % gw
-            if frame_ids is not None:
-                pf = frame_ids.long()[pf]
-            cs = torch.cat([rope_table[0, pf, :22], rope_table[1, ph, :21], rope_table[2, pw, :21]], dim=1)  # (n,64,2)
+            if tuple(grid) == (0, 0, 0):
+                cs = rope_table                                   # per-token mode: (n, 64, 2)
+            else:
+                idx = torch.arange(n) + token_offset
+                pf, ph, pw = (idx // (gh * gw)).clamp(max=gf - 1), (idx // gw) % gh, idx % gw   # pad rows of the last shard
+                if frame_ids is not None:
+                    pf = frame_ids.long()[pf]
+                cs = torch.cat([rope_table[0, pf, :22], rope_table[1, ph, :21], rope_table[2, pw, :21]], dim=1)  # (n,64,2)
             fr = torch.complex(cs[..., 0], cs[..., 1]).unsqueeze(1)                                          # (n,1,64)
             heads = t.shape[1] // 128
             yc = torch.view_as_complex(y.to(torch.float64).reshape(n, heads, 64, 2))

@@ -26,12 +26,20 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 14
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/wvd.h but not exported"
-    assert set(names) == set(_lib.SIGNATURES) | {"wvd_last_error"}
+    assert set(names) == set(_lib.SIGNATURES) | {"wvd_last_error", "wvd_build_info"}
+
+
+def test_library_was_built_from_the_sources_in_the_tree():
+    """The GPU box runs the libwvd.so that travelled with the snapshot: its baked-in source hash must be the hash of
+    the csrc/ + include/ files next to it (a stale prebuilt library fails here, on the CPU suite and on the box)."""
+    from video_styler_b200 import build
+    info = _lib.load().wvd_build_info().decode()
+    assert info.endswith("src=" + build.source_hash()), (info, build.source_hash())
 
 
 def test_version_and_arch():
     lib = _lib.load()
-    assert lib.wvd_version() >= 100
+    assert lib.wvd_version() >= 200
     assert lib.wvd_sm_arch() == 100
 
 
@@ -55,8 +63,10 @@ def test_argument_validation_without_gpu():
     ptrs = (ctypes.c_void_p * 8)(*([p] * 8))
     rc = lib.wvd_ulysses_scatter_qkv(p, 3 * 4 * 128, ptrs, 4, 4, 128, 9, 0, None)             # more than WVD_MAX_PEERS ranks
     assert rc == -1 and b"world" in lib.wvd_last_error()
-    rc = lib.wvd_attention_fwd_scatter(p, 128, p, 128, p, 128, ptrs, 256, 4, 200, 2, 1, 8, 8, 128, 0.1, None)   # columns past ldo
+    rc = lib.wvd_attention_fwd_scatter(p, 128, p, 128, p, 128, ptrs, 256, 4, 200, 2, 1, 8, 8, 128, 0.1, 0, None)   # columns past ldo
     assert rc == -1 and b"col_offset" in lib.wvd_last_error()
+    rc = lib.wvd_attention_fwd_select(p, 128, p, 128, p, 128, p, 128, 1, 8, 8, 128, 0.1, 7, None)               # unknown kernel
+    assert rc == -1 and b"selector" in lib.wvd_last_error()
     # empty inputs are accepted as no-ops
     assert lib.wvd_ln_modulate(p, 256, None, None, None, None, p, 256, 0, 256, 1e-6, 0, None) == 0
     assert lib.wvd_scale_add(p, p, 1.0, p, 0, 0, None) == 0

@@ -86,6 +86,34 @@ def test_rope_frame_ids_variant():
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_rope_per_token_table_and_padded_rows(dtype):
+    """(i) per-token mode: the reference's complex (N, 1, 64) freqs tensor as a (N, 64, 2) table gives the same bits
+    as the table + grid mode; (ii) rows past the token grid -- the zero padding of the last Ulysses shard
+    (wan_video_new.py:1414-1416; a ragged N on the LAST rank) -- are accepted, leave the real rows untouched and
+    produce finite values (they are never attended)."""
+    gf, gh, gw, d = 3, 5, 7, 512
+    n = gf * gh * gw
+    g = torch.Generator().manual_seed(3)
+    q, k = torch.randn(n, d, generator=g).to(dtype), torch.randn(n, d, generator=g).to(dtype)
+    w = (1 + 0.1 * torch.randn(d, generator=g)).to(dtype)
+    table = ops.make_rope_table(O.rope_tables_3d(128), DEV)
+    a_q, a_k = ops.qk_rmsnorm_rope(q.to(DEV), k.to(DEV), w.to(DEV), w.to(DEV), 1e-6, table, (gf, gh, gw), 0)
+    per_tok = ops.rope_table_from_freqs(O.rope_freqs(128, gf, gh, gw), DEV)
+    b_q, b_k = ops.qk_rmsnorm_rope(q.to(DEV), k.to(DEV), w.to(DEV), w.to(DEV), 1e-6, per_tok, (0, 0, 0), 0)
+    assert torch.equal(a_q, b_q) and torch.equal(a_k, b_k)
+    # last shard of a 2-rank split of n = 105 tokens: n_loc = 53, rank 1 holds rows [53, 105) + 1 pad row
+    n_loc = 53
+    shard = torch.zeros(n_loc, d, dtype=dtype)
+    shard[:n - n_loc] = q[n_loc:]
+    shard[n - n_loc:] = 7.0                                    # stale data in the pad row
+    c_q, _ = ops.qk_rmsnorm_rope(shard.to(DEV), None, w.to(DEV), None, 1e-6, table, (gf, gh, gw), n_loc)
+    assert torch.equal(c_q[:n - n_loc], a_q[n_loc:]) and torch.isfinite(c_q.float()).all()
+    with pytest.raises(_lib.WvdError):
+        ops.qk_rmsnorm_rope(shard.to(DEV), None, w.to(DEV), None, 1e-6, table, (gf, gh, gw), n + 1)     # offset outside the grid
+    _no_timeouts()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_residual_forms(dtype):
     x, y, gt = torch.randn(300, 512).to(dtype), torch.randn(300, 512).to(dtype), torch.randn(512).to(dtype)
     assert torch.equal(ops.scale_add(x.to(DEV), y.to(DEV), 0.75).cpu(), x + y * 0.75)
@@ -161,9 +189,7 @@ def _attn_ref(q, k, v, h, dtype=torch.float32):
 @pytest.fixture(params=[1, 2], ids=["two_tile_kernel", "cta_pair_kernel"])
 def attn_kernel(request):
     """Run the test on BOTH bf16 attention kernels (the default dispatch picks by key length)."""
-    _lib.check(_lib.load().wvd_debug_attention_kernel(request.param), "wvd_debug_attention_kernel")
-    yield request.param
-    _lib.check(_lib.load().wvd_debug_attention_kernel(0), "wvd_debug_attention_kernel")
+    return request.param
 
 
 @pytest.mark.parametrize("sq,sk,h", [(1, 1, 1), (128, 128, 1), (72, 72, 2), (256, 256, 2), (300, 512, 2), (257, 129, 3),
@@ -171,7 +197,7 @@ def attn_kernel(request):
 def test_attention_matches_oracle(sq, sk, h, attn_kernel):
     g = torch.Generator().manual_seed(sq + sk)
     q, k, v = (torch.randn(s, h * 128, generator=g).bfloat16() for s in (sq, sk, sk))
-    out = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), h)
+    out = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), h, kernel=attn_kernel)
     _no_timeouts()
     _close(out, _attn_ref(q, k, v, h), 4e-3)            # bf16 P / bf16 output rounding (same points as FA2)
 
@@ -188,7 +214,7 @@ def test_attention_repeated_launches_are_bit_identical(attn_kernel):
     ref = None
     for _ in range(40):
         junk.add_(1)
-        out = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h)
+        out = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h, kernel=attn_kernel)
         ref = out.clone() if ref is None else ref
         assert torch.equal(out, ref)
     _no_timeouts()
@@ -204,7 +230,7 @@ def test_attention_reads_fused_qkv_views_and_large_scores(attn_kernel):
     qkv = qkv.bfloat16()
     d = h * 128
     buf = qkv.to(DEV)
-    out = ops.attention(buf[:, :d], buf[:, d:2 * d], buf[:, 2 * d:], h)
+    out = ops.attention(buf[:, :d], buf[:, d:2 * d], buf[:, 2 * d:], h, kernel=attn_kernel)
     _no_timeouts()
     _close(out, _attn_ref(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h), 6e-3)
 
@@ -219,11 +245,11 @@ def test_attention_properties_at_full_length(attn_kernel, n):
     k = torch.randn(n, h * 128, device=DEV, generator=g).bfloat16()
     v = torch.randn(n, h * 128, device=DEV, generator=g).bfloat16()
     ones = torch.full_like(v, 0.5)
-    o1 = ops.attention(q, k, ones, h)
+    o1 = ops.attention(q, k, ones, h, kernel=attn_kernel)
     assert float((o1.float() - 0.5).abs().max()) <= 0.5 * 2 ** -7
-    out = ops.attention(q, k, v, h)
+    out = ops.attention(q, k, v, h, kernel=attn_kernel)
     perm = torch.randperm(n, device=DEV, generator=g)
-    outp = ops.attention(q, k[perm].contiguous(), v[perm].contiguous(), h)
+    outp = ops.attention(q, k[perm].contiguous(), v[perm].contiguous(), h, kernel=attn_kernel)
     assert O.parity_metrics(outp, out)["rel_l2"] <= 4e-3
     rows = torch.arange(0, n, 997, device=DEV)
     ref = _attn_ref(q[rows].cpu(), k.cpu(), v.cpu(), h) if False else \
@@ -285,6 +311,8 @@ def test_ulysses_peer_scatter_kernels_match_the_collective_layouts(world, heads,
         rv = recv[r]
         full = torch.zeros(world * n_loc, w, dtype=torch.bfloat16, device=DEV)
         ops.attention(rv[:n, :w], rv[:n, w:2 * w], rv[:n, 2 * w:], hl, out=full[:n])
+        # ... and the plain kernel itself against the fp32 oracle on the same operands (not only against itself)
+        _close(full[:n], _attn_ref(rv[:n, :w].cpu(), rv[:n, w:2 * w].cpu(), rv[:n, 2 * w:].cpu(), hl), 4e-3)
         for d in range(world):
             assert torch.equal(outs[d][:, r * w:(r + 1) * w], full[d * n_loc:(d + 1) * n_loc]), (r, d)
     _no_timeouts()

@@ -87,6 +87,45 @@ def test_block_and_hints_match_reference_intermediates(golden_dir):
             assert O.parity_metrics(got, ref)["rel_l2"] <= 1e-5
 
 
+def test_reference_block_signatures_with_complex_freqs(golden_dir):
+    """The reference's block-level call signatures (what wan_video_editor.py / training_loss-style callers use):
+    DiTBlock.forward(x, context, t_mod, freqs) with the COMPLEX (N, 1, 64) freqs tensor of wan_video_new.py:1392-1396
+    (wan_video_dit.py:214-230), and VaceWanAttentionBlock.forward(c, x, context, t_mod, freqs) with the stacked-tensor
+    protocol (wan_video_vace.py:13-24), against tensors captured from the real reference (fp32 mode)."""
+    fix = _load(golden_dir, "tiny_vace_lora")
+    dit, vace = build_models(fix, torch.float32, DEV)
+    cfg = O.DIT_CONFIGS["tiny"]
+    inp = O.make_inputs(fix["latent_shape"], cfg["text_dim"], seed=1, with_vace=True)
+    freqs = O.rope_freqs(128, 3, 4, 6).to(DEV)                     # complex128 (72, 1, 64), like the reference builds it
+    assert torch.is_complex(freqs) and freqs.shape == (72, 1, 64)
+    with torch.no_grad():
+        ctx = dit.text_embedding(inp["context"].to(DEV))
+        t_mod = fix["t_mod"].to(DEV)
+        x = fix["block0_in"].to(DEV)
+        y = dit.blocks[0](x, ctx, t_mod, freqs)
+        assert O.parity_metrics(y, fix["block0_out"])["rel_l2"] <= 1e-5
+        # VACE: drive the blocks one by one exactly like VaceWanModel.forward of the reference (wan_video_vace.py:64-86)
+        c = engine_patch(vace, inp["vace_context"].to(DEV))
+        for blk in vace.vace_blocks:
+            c = blk(c, x, ctx, t_mod, freqs)
+        hints = torch.unbind(c)[:-1]
+        assert len(hints) == len(fix["hints"])
+        for got, ref in zip(hints, fix["hints"]):
+            assert O.parity_metrics(got, ref)["rel_l2"] <= 1e-5
+        # RMSNorm.forward leaves its input alone (the reference module is out-of-place)
+        q = torch.randn(1, 72, 256, device=DEV)
+        q0 = q.clone()
+        out = dit.blocks[0].self_attn.norm_q(q)
+        assert torch.equal(q, q0) and out.shape == q.shape
+        assert O.parity_metrics(out, O.rms_norm(q0, dit.blocks[0].self_attn.norm_q.weight, 1e-6))["rel_l2"] <= 1e-6
+    assert _lib.debug_flags()["timeouts"] == 0
+
+
+def engine_patch(vace, vace_context):
+    from video_styler_b200 import engine
+    return engine.patch_embed(vace.vace_patch_embedding, vace_context).unsqueeze(0)
+
+
 def test_wanmodel_forward_equals_model_fn(golden_dir):
     """The fixed WanModel.forward (the reference's is stale) == model_fn_wan_video(dit, latents=x, ...)."""
     fix = _load(golden_dir, "tiny_t2v")

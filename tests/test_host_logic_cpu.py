@@ -178,3 +178,29 @@ def test_lora_loader_matches_the_reference_merge():
     # key forms of get_name_dict: adapter name optional, 'diffusion_model.' prefix dropped
     nd = V.GeneralLoRALoader().get_name_dict({"diffusion_model.vace_blocks.0.ffn.0.lora_B.weight": 0, "vace_blocks.1.self_attn.q.lora_B.default.weight": 0})
     assert set(nd) == {"vace_blocks.0.ffn.0", "vace_blocks.1.self_attn.q"}
+
+
+def test_block_with_reference_complex_freqs_and_padded_rope_rows(golden_dir):
+    """engine.as_rope_info: the reference's complex (N, 1, 64) freqs drive the block through the per-token RoPE mode
+    (same result as the table + grid mode); rows past the grid (padding of the last Ulysses shard) are tolerated."""
+    fix = _load(golden_dir, "tiny_vace_lora")
+    dit, _ = build_models(fix)
+    cfg = O.DIT_CONFIGS["tiny"]
+    inp = O.make_inputs(fix["latent_shape"], cfg["text_dim"], seed=1, with_vace=True)
+    with torch.no_grad():
+        ctx = dit.text_embedding(inp["context"])[0]
+        x = fix["block0_in"][0].clone()
+        ws = engine.workspace(x.shape[0], dit.dim, cfg["ffn_dim"], ctx.shape[0], x.dtype, x.device)
+        rope = engine.as_rope_info(O.rope_freqs(128, 3, 4, 6), "cpu", cpu_backend)
+        assert tuple(rope.grid) == (0, 0, 0) and rope.table.shape == (72, 64, 2)
+        y = engine.dit_block_forward(dit.blocks[0], x, ctx, fix["t_mod"], rope, ws, cpu_backend)
+    assert O.parity_metrics(y.unsqueeze(0), fix["block0_out"])["max_abs"] <= 5e-5
+    with pytest.raises(TypeError):
+        engine.as_rope_info(torch.zeros(72, 1, 64), "cpu", cpu_backend)
+    # padded rows: 80 rows on a 72-token grid starting at offset 0 -> rows 72..79 take the last frame's angles
+    tab = cpu_backend.make_rope_table(O.rope_tables_3d(128), "cpu")
+    q = torch.randn(80, 256)
+    w = torch.ones(256)
+    out, _ = cpu_backend.qk_rmsnorm_rope(q.clone(), None, w, None, 1e-6, tab, (3, 4, 6), 0)
+    ref, _ = cpu_backend.qk_rmsnorm_rope(q[:72].clone(), None, w, None, 1e-6, tab, (3, 4, 6), 0)
+    assert torch.equal(out[:72], ref) and torch.isfinite(out).all()

@@ -19,9 +19,7 @@ qkv = torch.randn(n, 3 * d, device="cuda", generator=g).bfloat16()
 table = ops.make_rope_table(O.rope_tables_3d(128), "cuda")
 ops.qk_rmsnorm_rope(qkv[:, :d], qkv[:, d:2 * d], gate, gate, 1e-6, table, (3, 10, 10), 0)
 for kern in (1, 2):
-    _lib.check(_lib.load().wvd_debug_attention_kernel(kern))
-    o = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h)
-_lib.check(_lib.load().wvd_debug_attention_kernel(0))
+    o = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h, kernel=kern)
 outs = [torch.zeros(150, d, dtype=torch.bfloat16, device="cuda") for _ in range(2)]
 recv = [torch.zeros(300, 3 * d // 2, dtype=torch.bfloat16, device="cuda") for _ in range(2)]
 ops.ulysses_scatter_qkv(qkv[:150].contiguous(), h, [t.data_ptr() for t in recv], 0)

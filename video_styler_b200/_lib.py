@@ -16,8 +16,6 @@ SIGNATURES = {
     "wvd_version": [],
     "wvd_sm_arch": [],
     "wvd_debug_flags": [ctypes.POINTER(ctypes.c_ulonglong)],
-    "wvd_debug_attention_profile": [c_void_p],
-    "wvd_debug_attention_kernel": [c_int],
     "wvd_ln_modulate": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                         c_float, c_int, c_void_p],
     "wvd_qk_rmsnorm_rope": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
@@ -31,18 +29,21 @@ SIGNATURES = {
                      c_int, c_void_p, c_void_p, c_int64, c_void_p],
     "wvd_attention_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64,
                           c_int64, c_int, c_float, c_void_p],
+    "wvd_attention_fwd_select": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64,
+                                 c_int64, c_int, c_float, c_int, c_void_p],
     "wvd_attention_fwd_f32": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int,
                               c_int64, c_int64, c_int, c_float, c_void_p],
     "wvd_ulysses_pack_qkv": [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
     "wvd_ulysses_unpack_out": [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p],
     "wvd_ulysses_scatter_qkv": [c_void_p, c_int64, ctypes.POINTER(c_void_p), c_int64, c_int, c_int, c_int, c_int, c_void_p],
     "wvd_attention_fwd_scatter": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, ctypes.POINTER(c_void_p), c_int64,
-                                  c_int64, c_int64, c_int, c_int, c_int64, c_int64, c_int, c_float, c_void_p],
+                                  c_int64, c_int64, c_int, c_int, c_int64, c_int64, c_int, c_float, c_int, c_void_p],
 }
 MAX_PEERS = 8
 
 WVD_BF16, WVD_F32 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_GATE_RES = 0, 1, 2, 3
+ATTN_AUTO, ATTN_TWO_TILE, ATTN_PAIR = 0, 1, 2
 
 _lib = None
 
@@ -62,6 +63,8 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.wvd_last_error.restype = ctypes.c_char_p
     lib.wvd_last_error.argtypes = []
+    lib.wvd_build_info.restype = ctypes.c_char_p
+    lib.wvd_build_info.argtypes = []
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError if the symbol is missing
         fn.restype = c_int

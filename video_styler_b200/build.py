@@ -33,6 +33,18 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
+def source_hash() -> str:
+    """sha256 over every file the library is compiled from (csrc/* and include/wvd.h), in sorted order: baked into
+    the library (wvd_build_info) so that a prebuilt libwvd.so can be checked against the sources it travels with."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    for f in files + [os.path.join(ROOT, "include", "wvd.h")]:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def _stale(target, deps):
     if not os.path.exists(target):
         return True
@@ -44,11 +56,17 @@ def build(force=False, verbose=False):
     nvcc = nvcc_path()
     os.makedirs(OBJ_DIR, exist_ok=True)
     jobs = []
+    all_src = [os.path.join(CSRC, x) for x in SOURCES]
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        if force or _stale(o, [s] + HEADERS + [os.path.abspath(__file__)]):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        deps = [s] + HEADERS + [os.path.abspath(__file__)]
+        extra = []
+        if src == "api.cu":          # carries the source hash of the whole library: rebuilt whenever any source changes
+            deps += all_src
+            extra = [f'-DWVD_SOURCE_HASH="{source_hash()}"']
+        if force or _stale(o, deps):
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append((src, cmd))
 
     def run(job):

@@ -118,11 +118,18 @@ int attn_pair_read_diag(unsigned long long* out);
 }  // namespace wvd
 
 extern "C" __attribute__((visibility("default"))) const char* wvd_last_error(void) { return wvd::last_error_ref().c_str(); }
-extern "C" __attribute__((visibility("default"))) int wvd_version(void) { return 100; /* 0.1.0 */ }
+extern "C" __attribute__((visibility("default"))) int wvd_version(void) { return 200; /* 0.2.0 */ }
+#ifndef WVD_SOURCE_HASH
+#define WVD_SOURCE_HASH "unknown"
+#endif
+extern "C" __attribute__((visibility("default"))) const char* wvd_build_info(void) {
+    return "wvd 0.2.0 sm_100a src=" WVD_SOURCE_HASH;
+}
 extern "C" __attribute__((visibility("default"))) int wvd_sm_arch(void) { return 100; }
 
 extern "C" __attribute__((visibility("default"))) int wvd_debug_flags(unsigned long long out[8]) {
     using namespace wvd;
+    // a kernel whose watchdog fired has trapped: the synchronise below then reports the sticky launch failure
     WVD_CHECK_CUDA(cudaDeviceSynchronize());
     unsigned long long a[8] = {0}, b[8] = {0}, c[8] = {0};
     if (gemm_read_diag(a) != 0 || attn_read_diag(b) != 0 || attn_pair_read_diag(c) != 0)

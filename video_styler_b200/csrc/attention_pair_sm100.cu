@@ -22,8 +22,8 @@
 //                       pair, ring of 3 pair slots (192 KB)
 //   warp 9 (1 thread)   MMA issuer: S_(j+2)%3 = Q K_{j+2}^T (SS) issued AHEAD of O += P_j V_j (TS); owns the TMEM allocation
 // Compile-time variants kept for A/B: WVD_ATTN2_PAIRSLOTS=0 (separate K / V slots and barriers),
-// WVD_ATTN2_QTMEM (Q in TMEM, two S buffers), WVD_ATTN2_HO0 (keys in the first P hand-over / 16), WVD_ATTN2_EXPERIMENT_*
-// (timing experiments that produce WRONG results on purpose).
+// WVD_ATTN2_QTMEM (Q in TMEM, two S buffers), WVD_ATTN2_HO0 (keys in the first P hand-over / 16).  All of them compute
+// the same result; the round-1 timing experiments that did not have been removed from the source.
 #include <math.h>
 #include <stdlib.h>
 
@@ -32,7 +32,9 @@
 #include "softmax_math.cuh"
 
 namespace wvd {
+#ifdef WVD_ATTN_PROF
 namespace attn { extern unsigned long long* g_prof_buffer; }
+#endif
 namespace attn2 {
 
 using attn::exp_chunk;
@@ -404,16 +406,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             tc_fence_after();
             PROF_LAP(pc_wait);
             uint32_t s[BKV];
-#ifdef WVD_ATTN2_EXPERIMENT_NO_LOAD       // timing experiment only (wrong results): what do the S loads from TMEM cost?
-            tmem_ld_32x32b_x32(s_tmem + 0, s + 0);
-#pragma unroll
-            for (int c = 32; c < BKV; ++c) s[c] = s[c & 31] + c;
-#else
             tmem_ld_32x32b_x32(s_tmem + 0, s + 0);
             tmem_ld_32x32b_x32(s_tmem + 32, s + 32);
             tmem_ld_32x32b_x32(s_tmem + 64, s + 64);
             tmem_ld_32x32b_x32(s_tmem + 96, s + 96);
-#endif
             tc_wait_ld();
             PROF_LAP(pc_ld);
             if (j == n_kv - 1 && tail_valid < BKV) {
@@ -421,11 +417,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 for (int c = 0; c < BKV; ++c)
                     if (c >= tail_valid) s[c] = 0xff800000u;   // -inf
             }
-#ifdef WVD_ATTN2_EXPERIMENT_PARTIAL_MAX      // timing experiment only (NOT exact): how much does the exact row maximum cost?
-            const float mx = row_max<BKV, 0, 32>(s, -INFINITY);
-#else
             const float mx = row_max<BKV, 0, BKV>(s, -INFINITY);     // exact row maximum of this tile
-#endif
 #ifdef WVD_ATTN_PROF
             if (prof) { uint32_t t_; asm volatile("mov.u32 %0, %%clock;" : "=r"(t_)); t_ += __float_as_uint(mx) & 0u; pc_max += t_ - pt; pt = t_; }
 #endif
@@ -486,9 +478,6 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     case 6: lsum += exp_chunk<BKV, 6 * GC, 7 * GC, EMU_OF_4>(s, pk, sl2_2, negm_2); break;
                     default: lsum += exp_chunk<BKV, 7 * GC, 8 * GC, EMU_OF_4>(s, pk, sl2_2, negm_2); break;
                 }
-#ifdef WVD_ATTN2_EXPERIMENT_NO_STORE      // timing experiment only (wrong results): what do the P stores to TMEM cost?
-                if (q8 == 0 || __float_as_uint(lsum) == 0x12345678u)
-#endif
                 store_p<GC / 2>(s_tmem + q8 * (GC / 2), pk);
                 if (q8 == HO0_GROUPS - 1 || q8 == BKV / GC - 1) {
                     tc_wait_st();
@@ -563,7 +552,7 @@ int attn_pair_read_diag(unsigned long long* out) {
 // Launch the CTA-pair kernel.  Same contract as wvd::attn::launch (attention_sm100.cu), which validates the arguments.
 int attention_pair_launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                           void* const* out_peers, int world, int64_t rows_per_peer, int64_t ldo, int num_heads,
-                          int64_t sq, int64_t sk, float scale, int emu, cudaStream_t st) {
+                          int64_t sq, int64_t sk, float scale, cudaStream_t st) {
     using namespace attn2;
     const int64_t width = (int64_t)num_heads * HD;
     CUtensorMap tmQ, tmK, tmV;
@@ -588,17 +577,18 @@ int attention_pair_launch(const void* q, int64_t ldq, const void* k, int64_t ldk
     p.sk = (int)sk;
     p.n_kv = (int)((sk + BKV - 1) / BKV);
     p.scale_log2 = scale * 1.4426950408889634f;
+#ifdef WVD_ATTN_PROF
     p.prof = attn::g_prof_buffer;
+#else
+    p.prof = nullptr;
+#endif
     static unsigned long long configured = 0;
-    if (first_use_on_current_device(&configured)) {
+    if (first_use_on_current_device(&configured))
         WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    }
     unsigned q_tiles = (unsigned)((sq + BQ - 1) / BQ);
     q_tiles = (q_tiles + 1u) & ~1u;          // whole CTA pairs; a surplus CTA computes rows >= sq and stores nothing
     dim3 grid(q_tiles, (unsigned)num_heads);
-    if (emu == 0) attention_pair_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
-    else attention_pair_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+    attention_pair_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
     WVD_CHECK_CUDA(cudaGetLastError());
     return WVD_OK;
 }

@@ -420,8 +420,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (warp == ALLOC_WARP) tmem_dealloc(tmem_base, 512);
 }
 
-unsigned long long* g_prof_buffer = nullptr;
-int g_kernel_select = -1;      // -1 = not yet read from WVD_ATTN_KERNEL; see wvd_debug_attention_kernel
+#ifdef WVD_ATTN_PROF
+unsigned long long* g_prof_buffer = nullptr;      // developer builds only (-DWVD_ATTN_PROF): in-kernel phase counters
+#endif
 }  // namespace attn
 
 int attn_read_diag(unsigned long long* out) {
@@ -433,26 +434,23 @@ int attn_read_diag(unsigned long long* out) {
 
 }  // namespace wvd
 
-extern "C" __attribute__((visibility("default"))) int wvd_debug_attention_kernel(int which) {
-    WVD_REQUIRE(which >= 0 && which <= 2, "wvd_debug_attention_kernel: 0 = by key length, 1 = two-tile, 2 = CTA-pair");
-    wvd::attn::g_kernel_select = which;
-    return WVD_OK;
-}
-
+#ifdef WVD_ATTN_PROF
 extern "C" __attribute__((visibility("default"))) int wvd_debug_attention_profile(unsigned long long* device_buf) {
     wvd::attn::g_prof_buffer = device_buf;
     return WVD_OK;
 }
+#endif
 
 namespace wvd {
 int attention_pair_launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                           void* const* out_peers, int world, int64_t rows_per_peer, int64_t ldo, int num_heads,
-                          int64_t sq, int64_t sk, float scale, int emu, cudaStream_t st);
+                          int64_t sq, int64_t sk, float scale, cudaStream_t st);
 namespace attn {
 static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                   void* const* out_peers, int world, int64_t rows_per_peer, int64_t ldo, int num_heads, int64_t sq,
-                  int64_t sk, int head_dim, float scale, wvd_stream_t stream) {
+                  int64_t sk, int head_dim, float scale, int which, wvd_stream_t stream) {
     WVD_REQUIRE(q && k && v && (out || out_peers), "wvd_attention_fwd: null pointer");
+    WVD_REQUIRE(which >= WVD_ATTN_AUTO && which <= WVD_ATTN_PAIR, "wvd_attention_fwd: bad kernel selector %d", which);
     WVD_REQUIRE(head_dim == HD, "wvd_attention_fwd: head_dim must be 128 (got %d)", head_dim);
     WVD_REQUIRE(num_heads > 0 && num_heads <= 65535, "wvd_attention_fwd: bad num_heads %d", num_heads);
     WVD_REQUIRE(sq > 0 && sk > 0 && sq < (1ll << 31) && sk < (1ll << 31), "wvd_attention_fwd: bad sequence lengths sq=%lld sk=%lld", (long long)sq, (long long)sk);
@@ -486,40 +484,25 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
     p.sk = (int)sk;
     p.n_kv = (int)((sk + BKV - 1) / BKV);
     p.scale_log2 = scale * 1.4426950408889634f;
+#ifdef WVD_ATTN_PROF
     p.prof = g_prof_buffer;
-    static int emu = -1;
-    if (emu < 0) {
-        const char* e = getenv("WVD_ATTN_EMU");        // tuning knob: 0..3 of every 4 column pairs on the FMA pipes
-        int ev = e ? atoi(e) : 0;          // measured on B200: 0 is fastest (the softmax is issue-bound, not MUFU-bound)
-        emu = ev < 0 ? 0 : (ev > 3 ? 3 : ev);
-    }
+#else
+    p.prof = nullptr;
+#endif
     static unsigned long long configured = 0;
-    if (first_use_on_current_device(&configured)) {
+    if (first_use_on_current_device(&configured))
         WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        WVD_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    }
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_kernel_select < 0) {
-        const char* e = getenv("WVD_ATTN_KERNEL");     // developer A/B: force kernel 1 or 2
-        g_kernel_select = e ? atoi(e) : WVD_ATTN_KERNEL_DEFAULT;
-    }
-    const int which = g_kernel_select;
     // Long key sequences (self-attention) go to the CTA-pair kernel (attention_pair_sm100.cu: one Q tile per CTA,
     // triple-buffered S, K/V multicast across a 2-CTA cluster): 1-2 % faster than this kernel in sustained runs and
     // 2.4 % faster per launch inside the c3 step.  Short ones (the 512-token text cross-attention: 4 KV steps,
-    // prologue-dominated, 0.49 vs 0.73 ms) stay on the two-tile kernel of this file.
-    if (which == 2 || (which == 0 && sk >= 2048))
+    // prologue-dominated) stay on the two-tile kernel of this file.  `which` is an explicit ARGUMENT (the parity
+    // tests run both kernels on the same inputs): the library keeps no mutable selection state.
+    if (which == WVD_ATTN_PAIR || (which == WVD_ATTN_AUTO && sk >= 2048))
         return attention_pair_launch(q, ldq, k, ldk, v, ldv, out, out_peers ? (void* const*)p.out_peer : nullptr, world,
-                                     rows_per_peer, ldo, num_heads, sq, sk, scale, emu, st);
+                                     rows_per_peer, ldo, num_heads, sq, sk, scale, st);
     dim3 grid((unsigned)((sq + QT * BQ - 1) / (QT * BQ)), (unsigned)num_heads);
-    switch (emu) {
-        case 0: attention_fwd_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-        case 1: attention_fwd_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-        case 2: attention_fwd_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-        default: attention_fwd_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-    }
+    attention_fwd_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
     WVD_CHECK_CUDA(cudaGetLastError());
     return WVD_OK;
 }
@@ -530,7 +513,16 @@ extern "C" __attribute__((visibility("default"))) int wvd_attention_fwd(const vo
                                  void* out, int64_t ldo, int num_heads, int64_t sq, int64_t sk, int head_dim,
                                  float scale, wvd_stream_t stream) {
     WVD_REQUIRE(out, "wvd_attention_fwd: null pointer");
-    return wvd::attn::launch(q, ldq, k, ldk, v, ldv, out, nullptr, 1, 0, ldo, num_heads, sq, sk, head_dim, scale, stream);
+    return wvd::attn::launch(q, ldq, k, ldk, v, ldv, out, nullptr, 1, 0, ldo, num_heads, sq, sk, head_dim, scale,
+                             WVD_ATTN_AUTO, stream);
+}
+
+// The same contraction on an explicitly named kernel (parity tests run both kernels on the same inputs).
+extern "C" __attribute__((visibility("default"))) int wvd_attention_fwd_select(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                        void* out, int64_t ldo, int num_heads, int64_t sq, int64_t sk, int head_dim,
+                                        float scale, int which, wvd_stream_t stream) {
+    WVD_REQUIRE(out, "wvd_attention_fwd_select: null pointer");
+    return wvd::attn::launch(q, ldq, k, ldk, v, ldv, out, nullptr, 1, 0, ldo, num_heads, sq, sk, head_dim, scale, which, stream);
 }
 
 // Ulysses return trip fused into the attention epilogue: out_ptrs[r] is rank r's (rows_per_peer, ldo) output buffer
@@ -538,7 +530,7 @@ extern "C" __attribute__((visibility("default"))) int wvd_attention_fwd(const vo
 extern "C" __attribute__((visibility("default"))) int wvd_attention_fwd_scatter(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                          int64_t ldv, void* const* out_ptrs, int64_t ldo, int64_t rows_per_peer,
                                          int64_t col_offset, int world, int num_heads, int64_t sq, int64_t sk,
-                                         int head_dim, float scale, wvd_stream_t stream) {
+                                         int head_dim, float scale, int which, wvd_stream_t stream) {
     WVD_REQUIRE(out_ptrs && world >= 1 && world <= WVD_MAX_PEERS, "wvd_attention_fwd_scatter: bad peers");
     WVD_REQUIRE(col_offset >= 0 && col_offset % 8 == 0 && col_offset + (int64_t)num_heads * head_dim <= ldo,
                 "wvd_attention_fwd_scatter: bad col_offset");
@@ -546,5 +538,5 @@ extern "C" __attribute__((visibility("default"))) int wvd_attention_fwd_scatter(
     for (int r = 0; r < world; ++r) shifted[r] = out_ptrs[r] ? (void*)((__nv_bfloat16*)out_ptrs[r] + col_offset) : nullptr;
     // the leading-dimension check of launch() is against the local head count only
     return wvd::attn::launch(q, ldq, k, ldk, v, ldv, nullptr, shifted, world, rows_per_peer, ldo, num_heads, sq, sk, head_dim,
-                             scale, stream);
+                             scale, which, stream);
 }

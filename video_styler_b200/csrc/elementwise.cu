@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (MAXV <= 20 ? 2 : 1))
 qk_rmsnorm_rope_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ k, long long ldk,
                        const T* __restrict__ wq, const T* __restrict__ wk, T* __restrict__ qo, long long ldqo,
                        T* __restrict__ ko, long long ldko, long long n_tokens, int dim, float eps,
-                       const float2* __restrict__ rope_cs, const int* __restrict__ frame_ids, int gh, int gw,
+                       const float2* __restrict__ rope_cs, const int* __restrict__ frame_ids, int gf, int gh, int gw,
                        long long token_offset) {
     constexpr int VE = VecIO<T>::N;
     const int lane = threadIdx.x & 31;
@@ -295,20 +295,29 @@ qk_rmsnorm_rope_kernel(const T* __restrict__ q, long long ldq, const T* __restri
     float2 cs[VE / 2];
     if (ROPE) {
         // this lane always owns the same pairs of every head: channel (lane*VE) % 128 (+ 0..VE-1)
-        const long long n = token_offset + row;
-        const int pw = static_cast<int>(n % gw);
-        const int ph = static_cast<int>((n / gw) % gh);
-        int pf = static_cast<int>(n / (static_cast<long long>(gw) * gh));
-        if (frame_ids != nullptr) pf = frame_ids[pf];
         const int pair0 = ((lane * VE) % 128) / 2;
+        if (gf == 0) {
+            // per-token mode: rope_cs is (n_tokens, 64) (cos, sin) -- the reference's `freqs` tensor (N, 1, 64) complex
+            // as DiTBlock.forward receives it (wan_video_dit.py:214-230), cast to fp32 pairs by the binding
 #pragma unroll
-        for (int pr = 0; pr < VE / 2; ++pr) {
-            const int j = pair0 + pr;
-            int axis, jj, pos;
-            if (j < 22) { axis = 0; jj = j; pos = pf; }
-            else if (j < 43) { axis = 1; jj = j - 22; pos = ph; }
-            else { axis = 2; jj = j - 43; pos = pw; }
-            cs[pr] = __ldg(rope_cs + (static_cast<long long>(axis) * 1024 + pos) * 32 + jj);
+            for (int pr = 0; pr < VE / 2; ++pr) cs[pr] = __ldg(rope_cs + row * 64 + pair0 + pr);
+        } else {
+            const long long n = token_offset + row;
+            const int pw = static_cast<int>(n % gw);
+            const int ph = static_cast<int>((n / gw) % gh);
+            // rows past the grid are the zero padding of the last Ulysses shard (wan_video_new.py:1414-1416): they are
+            // never attended nor returned, any valid table entry will do
+            int pf = min(static_cast<int>(n / (static_cast<long long>(gw) * gh)), gf - 1);
+            if (frame_ids != nullptr) pf = frame_ids[pf];
+#pragma unroll
+            for (int pr = 0; pr < VE / 2; ++pr) {
+                const int j = pair0 + pr;
+                int axis, jj, pos;
+                if (j < 22) { axis = 0; jj = j; pos = pf; }
+                else if (j < 43) { axis = 1; jj = j - 22; pos = ph; }
+                else { axis = 2; jj = j - 43; pos = pw; }
+                cs[pr] = __ldg(rope_cs + (static_cast<long long>(axis) * 1024 + pos) * 32 + jj);
+            }
         }
     }
     if (blockIdx.y == 0) rms_rope_row<T, MAXV, ROPE>(q + row * ldq, wq, qo + row * ldqo, dim, eps, lane, cs);
@@ -318,17 +327,17 @@ qk_rmsnorm_rope_kernel(const T* __restrict__ q, long long ldq, const T* __restri
 template <typename T, int MAXV>
 int launch_rms(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* wq, const void* wk, void* qo,
                int64_t ldqo, void* ko, int64_t ldko, int64_t n, int dim, float eps, const void* rope_cs,
-               const int32_t* frame_ids, int gh, int gw, int64_t token_offset, cudaStream_t s) {
+               const int32_t* frame_ids, int gf, int gh, int gw, int64_t token_offset, cudaStream_t s) {
     const dim3 grid(static_cast<unsigned>((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), k != nullptr ? 2 : 1);
     const dim3 block(WARPS_PER_BLOCK * 32);
     if (rope_cs != nullptr)
         qk_rmsnorm_rope_kernel<T, MAXV, true><<<grid, block, 0, s>>>(
             (const T*)q, ldq, (const T*)k, ldk, (const T*)wq, (const T*)wk, (T*)qo, ldqo, (T*)ko, ldko, n, dim, eps,
-            (const float2*)rope_cs, frame_ids, gh, gw, token_offset);
+            (const float2*)rope_cs, frame_ids, gf, gh, gw, token_offset);
     else
         qk_rmsnorm_rope_kernel<T, MAXV, false><<<grid, block, 0, s>>>(
             (const T*)q, ldq, (const T*)k, ldk, (const T*)wq, (const T*)wk, (T*)qo, ldqo, (T*)ko, ldko, n, dim, eps,
-            nullptr, nullptr, 1, 1, 0);
+            nullptr, nullptr, 1, 1, 1, 0);
     WVD_CHECK_CUDA(cudaGetLastError());
     return WVD_OK;
 }
@@ -495,22 +504,29 @@ extern "C" __attribute__((visibility("default"))) int wvd_qk_rmsnorm_rope(const 
                 "wvd_qk_rmsnorm_rope: pointers must be 16-byte aligned");
     if (n_tokens == 0) return WVD_OK;
     WVD_REQUIRE(n_tokens > 0, "wvd_qk_rmsnorm_rope: negative n_tokens");
-    if (rope_cs) {
+    if (rope_cs && grid_f == 0) {
+        // per-token cos/sin table (n_tokens, 64) float2: the reference's complex `freqs` argument of DiTBlock.forward
+        WVD_REQUIRE(grid_h == 0 && grid_w == 0 && frame_ids == nullptr && token_offset == 0,
+                    "wvd_qk_rmsnorm_rope: per-token rope table (grid 0x0x0) takes no grid / frame_ids / token_offset");
+        grid_h = grid_w = 1;
+    } else if (rope_cs) {
         WVD_REQUIRE(grid_f > 0 && grid_h > 0 && grid_w > 0 && grid_h <= 1024 && grid_w <= 1024,
                     "wvd_qk_rmsnorm_rope: bad token grid %dx%dx%d", grid_f, grid_h, grid_w);
-        WVD_REQUIRE(token_offset >= 0 && token_offset + n_tokens <= (int64_t)grid_f * grid_h * grid_w,
-                    "wvd_qk_rmsnorm_rope: tokens [%lld,%lld) exceed the %dx%dx%d grid", (long long)token_offset,
-                    (long long)(token_offset + n_tokens), grid_f, grid_h, grid_w);
+        // rows in [grid, token_offset + n_tokens) are tolerated only as the padding of the LAST shard: fewer than one
+        // shard's worth of them (n_tokens), the reference's pad-to-ceil(N/P) (wan_video_new.py:1414-1416)
+        WVD_REQUIRE(token_offset >= 0 && token_offset <= (int64_t)grid_f * grid_h * grid_w,
+                    "wvd_qk_rmsnorm_rope: token_offset %lld is outside the %dx%dx%d grid", (long long)token_offset,
+                    grid_f, grid_h, grid_w);
         WVD_REQUIRE(frame_ids != nullptr || grid_f <= 1024, "wvd_qk_rmsnorm_rope: more than 1024 frames");
     }
     const int need = (dim / ve + 31) / 32;
     cudaStream_t s = (cudaStream_t)stream;
 #define WVD_DISPATCH(T)                                                                                                \
-    if (need <= 2) return ew::launch_rms<T, 2>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_h, grid_w, token_offset, s);   \
-    if (need <= 6) return ew::launch_rms<T, 6>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_h, grid_w, token_offset, s);   \
-    if (need <= 12) return ew::launch_rms<T, 12>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_h, grid_w, token_offset, s); \
-    if (need <= 20) return ew::launch_rms<T, 20>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_h, grid_w, token_offset, s); \
-    if (need <= 40) return ew::launch_rms<T, 40>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_h, grid_w, token_offset, s);
+    if (need <= 2) return ew::launch_rms<T, 2>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_f, grid_h, grid_w, token_offset, s);   \
+    if (need <= 6) return ew::launch_rms<T, 6>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_f, grid_h, grid_w, token_offset, s);   \
+    if (need <= 12) return ew::launch_rms<T, 12>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_f, grid_h, grid_w, token_offset, s); \
+    if (need <= 20) return ew::launch_rms<T, 20>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_f, grid_h, grid_w, token_offset, s); \
+    if (need <= 40) return ew::launch_rms<T, 40>(q, ldq, k, ldk, wq, wk, q_out, ldqo, k_out, ldko, n_tokens, dim, eps, rope_cs, frame_ids, grid_f, grid_h, grid_w, token_offset, s);
     if (dtype == WVD_BF16) { WVD_DISPATCH(__nv_bfloat16) } else { WVD_DISPATCH(float) }
 #undef WVD_DISPATCH
     return set_error(WVD_ERR_UNSUPPORTED, "wvd_qk_rmsnorm_rope: dim %d too large", dim);

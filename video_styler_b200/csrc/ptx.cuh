@@ -6,13 +6,14 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace wvd {
 
 // --------------------------------------------------------------------------------------------
-// diagnostics: a bounded mbarrier wait never hangs the GPU.  On timeout it records which barrier
-// timed out in g_diag and falls through (the kernel then finishes with garbage, the host-side
-// tests read the flag through wvd_debug_flags()).
+// diagnostics: a bounded mbarrier wait never hangs the GPU and never lets a kernel finish with garbage.  On timeout
+// it records which barrier timed out in g_diag (first culprit only) and TRAPS: the launch fails with a sticky CUDA
+// error, so the next C-ABI call on the context returns WVD_ERR_CUDA and the Python binding raises WvdError.
 // --------------------------------------------------------------------------------------------
 static __device__ unsigned long long g_diag[8];   // [0]=timeout count, [1]=last tag, [2]=block, [3]=thread
 
@@ -91,7 +92,10 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 static __device__ __noinline__ void mbar_timeout(uint32_t tag) {
     if (atomicAdd(&g_diag[0], 1ull) == 0ull) {      // the FIRST timeout is the culprit, the rest cascade from it
         g_diag[1] = tag; g_diag[2] = blockIdx.x; g_diag[3] = threadIdx.x;
+        printf("wvd: mbarrier wait timed out (tag 0x%x, block %d, thread %d) -- aborting the kernel\n", tag, (int)blockIdx.x, (int)threadIdx.x);
     }
+    __threadfence_system();
+    __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag) {
     uint32_t spins = 0;

@@ -26,10 +26,16 @@ Tensor = torch.Tensor
 @dataclass
 class RopeInfo:
     """3-D RoPE addressing for the fused QK-RMSNorm+RoPE kernel (wan_video_new.py:1392-1396)."""
-    table: Tensor                      # (3, 1024, 32, 2) fp32 cos/sin
+    table: Tensor                      # (3, 1024, 32, 2) fp32 cos/sin; per-token mode: (N, 64, 2) with grid (0, 0, 0)
     grid: Tuple[int, int, int]         # (f, h, w) token grid
     token_offset: int = 0              # global index of local row 0 (Ulysses shard)
     frame_ids: Optional[Tensor] = None  # int32 (f,) -- rope_indices (wan_video_dit.py:378-384)
+
+    @staticmethod
+    def from_freqs(freqs: Tensor, device, ops=_cuda_ops) -> "RopeInfo":
+        """The reference's per-token ``freqs`` argument -- (N, 1, 64) complex, assembled at wan_video_new.py:1392-1396
+        and handed to ``block(x, context, t_mod, freqs)`` -- for callers that drive blocks directly."""
+        return RopeInfo(ops.rope_table_from_freqs(freqs, device), (0, 0, 0))
 
 
 @dataclass
@@ -111,6 +117,16 @@ def block_modulation(block, t_mod: Tensor) -> Tensor:
     if t_mod.dim() != 3 or t_mod.shape[0] != 1:
         raise NotImplementedError("per-token / batched t_mod (seperated_timestep) is not supported by the wvd path")
     return (block.modulation.to(dtype=t_mod.dtype, device=t_mod.device) + t_mod)[0].contiguous()
+
+
+def as_rope_info(freqs, device, ops=_cuda_ops) -> RopeInfo:
+    """``freqs`` as the blocks' callers pass it: an engine.RopeInfo (model_fn / WanModel.rope_info) or the reference's
+    complex per-token tensor."""
+    if isinstance(freqs, RopeInfo):
+        return freqs
+    if torch.is_tensor(freqs) and torch.is_complex(freqs):
+        return RopeInfo.from_freqs(freqs, device, ops)
+    raise TypeError("freqs must be an engine.RopeInfo (WanModel.rope_info) or the reference's complex (N, 1, 64) tensor")
 
 
 class SelfAttnExchange:

@@ -101,6 +101,16 @@ def make_rope_table(freqs: Tuple[Tensor, Tensor, Tensor], device) -> Tensor:
     return tab.to(device).contiguous()
 
 
+def rope_table_from_freqs(freqs: Tensor, device) -> Tensor:
+    """The reference's per-token ``freqs`` tensor -- (N, 1, 64) complex, what DiTBlock.forward / rope_apply take
+    (wan_video_dit.py:92-97, wan_video_new.py:1392-1396) -- as the (N, 64, 2) fp32 (cos, sin) table of the kernel's
+    per-token mode."""
+    if not torch.is_complex(freqs) or freqs.shape[-1] != 64:
+        raise WvdError(f"freqs must be a complex (N, 1, 64) tensor, got {tuple(freqs.shape)} {freqs.dtype}")
+    f = freqs.reshape(-1, 64)
+    return torch.stack([f.real, f.imag], dim=-1).to(device=device, dtype=torch.float32).contiguous()
+
+
 def qk_rmsnorm_rope(q: Tensor, k: Optional[Tensor], wq: Tensor, wk: Optional[Tensor], eps: float,
                     rope_table: Optional[Tensor] = None, grid: Tuple[int, int, int] = (1, 1, 1),
                     token_offset: int = 0, frame_ids: Optional[Tensor] = None,
@@ -116,7 +126,12 @@ def qk_rmsnorm_rope(q: Tensor, k: Optional[Tensor], wq: Tensor, wk: Optional[Ten
             raise WvdError("q and k must have the same shape/dtype (process the cross-attention k separately)")
         k_out = k if k_out is None else _chk2d(k_out, "k_out")
         wk = _vec(wk, d, "norm_k.weight", q)
-    if rope_table is not None:
+    if rope_table is not None and tuple(grid) == (0, 0, 0):
+        if rope_table.dtype != torch.float32 or tuple(rope_table.shape) != (n, 64, 2) or not rope_table.is_cuda or not rope_table.is_contiguous():
+            raise WvdError("per-token rope table must be a contiguous (n_tokens, 64, 2) fp32 CUDA tensor (see rope_table_from_freqs)")
+        if frame_ids is not None or token_offset != 0:
+            raise WvdError("per-token rope table takes no frame_ids / token_offset")
+    elif rope_table is not None:
         if rope_table.dtype != torch.float32 or tuple(rope_table.shape) != (3, 1024, 32, 2) or not rope_table.is_cuda:
             raise WvdError("rope_table must be the (3,1024,32,2) fp32 CUDA table from make_rope_table()")
         if frame_ids is not None and (frame_ids.dtype != torch.int32 or not frame_ids.is_cuda):
@@ -161,8 +176,9 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, epilogue: i
 
 
 def attention(q: Tensor, k: Tensor, v: Tensor, num_heads: int, out: Optional[Tensor] = None,
-              scale: Optional[float] = None) -> Tensor:
-    """softmax(q k^T / sqrt(128)) v per head; q (Sq, H*128), k/v (Sk, H*128) views (wan_video_dit.py:28-61)."""
+              scale: Optional[float] = None, kernel: int = _lib.ATTN_AUTO) -> Tensor:
+    """softmax(q k^T / sqrt(128)) v per head; q (Sq, H*128), k/v (Sk, H*128) views (wan_video_dit.py:28-61).
+    ``kernel`` names one of the two bf16 kernels explicitly (parity tests); the default picks by key length."""
     q, k, v = _chk2d(q, "q"), _chk2d(k, "k"), _chk2d(v, "v")
     sq, width = q.shape
     sk = k.shape[0]
@@ -173,7 +189,6 @@ def attention(q: Tensor, k: Tensor, v: Tensor, num_heads: int, out: Optional[Ten
         out = torch.empty((sq, width), dtype=q.dtype, device=q.device)
     _chk2d(out, "out")
     scale = 1.0 / math.sqrt(128.0) if scale is None else scale
-    fn = _lib.load().wvd_attention_fwd if q.dtype == torch.bfloat16 else _lib.load().wvd_attention_fwd_f32
     _dt(q)
     if sq == 0:
         return out
@@ -183,8 +198,14 @@ def attention(q: Tensor, k: Tensor, v: Tensor, num_heads: int, out: Optional[Ten
     if prof:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(fn(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(), _ld(out), num_heads, sq,
-             sk, 128, scale, _stream()), "wvd_attention_fwd")
+    args = (q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(), _ld(out), num_heads, sq,
+            sk, 128, scale)
+    if q.dtype != torch.bfloat16:
+        check(_lib.load().wvd_attention_fwd_f32(*args, _stream()), "wvd_attention_fwd_f32")
+    elif kernel == _lib.ATTN_AUTO:
+        check(_lib.load().wvd_attention_fwd(*args, _stream()), "wvd_attention_fwd")
+    else:
+        check(_lib.load().wvd_attention_fwd_select(*args, kernel, _stream()), "wvd_attention_fwd_select")
     if prof:
         e1.record()
         PROFILE.setdefault("self_attention", []).append((e0, e1, num_heads, sq))
@@ -263,7 +284,7 @@ def ulysses_scatter_qkv(qkv: Tensor, heads: int, recv_ptrs, rank: int) -> None:
 
 
 def attention_scatter(q: Tensor, k: Tensor, v: Tensor, num_heads: int, out_ptrs, ldo: int, rows_per_peer: int,
-                      col_offset: int, scale: Optional[float] = None) -> None:
+                      col_offset: int, scale: Optional[float] = None, kernel: int = _lib.ATTN_AUTO) -> None:
     """ops.attention over the local heads whose epilogue stores query row t into rank t // rows_per_peer's
     (rows_per_peer, ldo) buffer at columns [col_offset, col_offset + num_heads*128) (peer pointers, NVLink): the
     Ulysses return all-to-all fused into the attention kernel.  The caller issues a cross-rank barrier afterwards."""
@@ -281,7 +302,7 @@ def attention_scatter(q: Tensor, k: Tensor, v: Tensor, num_heads: int, out_ptrs,
         e0.record()
     check(_lib.load().wvd_attention_fwd_scatter(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v),
                                                 _ptr_array(out_ptrs), ldo, rows_per_peer, col_offset, len(out_ptrs),
-                                                num_heads, sq, sk, 128, scale, _stream()), "wvd_attention_fwd_scatter")
+                                                num_heads, sq, sk, 128, scale, kernel, _stream()), "wvd_attention_fwd_scatter")
     if prof:
         e1.record()
         PROFILE.setdefault("self_attention", []).append((e0, e1, num_heads, sq))

@@ -80,6 +80,7 @@ class P2PUlyssesExchange(UlyssesExchange):
         super().__init__(group, n_tokens)
         self._bufs = {}
         self._nccl_only = False
+        self._probed = None
 
     def _buffers(self, n_loc: int, heads: int, device):
         key = (n_loc, heads)
@@ -99,29 +100,47 @@ class P2PUlyssesExchange(UlyssesExchange):
             self._bufs[key] = (recv, aout, h_recv, h_out, [int(x) for x in h_recv.buffer_ptrs], [int(x) for x in h_out.buffer_ptrs])
         return self._bufs[key]
 
+    def _probe(self, device) -> bool:
+        """Can EVERY rank take the peer-memory path?  Local, failure-free checks (symmetric-memory module importable,
+        peer access to every GPU of the group) agreed on with one all-reduce BEFORE anybody enters the rendezvous:
+        the rendezvous is itself a collective, so a rank that failed on its own on the way in would leave the others
+        blocked inside it.  After a unanimous yes, a failure inside the rendezvous is not recoverable by falling back
+        (the peers may already be waiting in it) and is raised."""
+        ok = 1
+        try:
+            import importlib
+            importlib.import_module("torch.distributed._symmetric_memory")
+            me = torch.device(device).index
+            me = torch.cuda.current_device() if me is None else me
+            devs = [None] * self.world
+            dist.all_gather_object(devs, (me, _host_id()), group=self.group)
+            for d, host in devs:
+                if host != _host_id() or (d != me and not torch.cuda.can_device_access_peer(me, d)):
+                    ok = 0
+        except Exception as e:      # noqa: BLE001 -- any local failure of the optional fast path selects the baseline
+            ok = 0
+            import warnings
+            warnings.warn(f"peer-memory Ulysses exchange unavailable on this rank ({e!r})")
+        flag = torch.tensor([ok], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return int(flag.item()) == 1
+
     def _buffers_or_none(self, n_loc: int, heads: int, device):
-        """The symmetric buffers, or None if the rendezvous is not possible on this box (no peer access, symmetric
-        memory unsupported ...).  The verdict is agreed on by all ranks (the rendezvous is a collective), and the
-        exchange then stays on NCCL collectives for good -- still the GPU path, just not the fused one."""
+        """The symmetric buffers, or None if this box cannot take the peer-memory path (agreed on by all ranks in
+        ``_probe``); the exchange then stays on NCCL collectives for good -- still the GPU path, just not the fused one."""
         if self._nccl_only:
             return None
         key = (n_loc, heads)
         if key in self._bufs:
             return self._bufs[key]
-        ok = torch.ones(1, device=device, dtype=torch.int32)
-        try:
-            bufs = self._buffers(n_loc, heads, device)
-        except Exception as e:      # noqa: BLE001 -- any failure of the optional fast path selects the baseline
-            bufs = None
-            ok.zero_()
-            import warnings
-            warnings.warn(f"peer-memory Ulysses exchange unavailable ({e!r}); using NCCL all_to_all")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
-        if int(ok.item()) == 0:
+        if self._probed is None:
+            self._probed = self._probe(device)
+        if not self._probed:
             self._nccl_only = True
-            self._bufs.pop(key, None)
+            import warnings
+            warnings.warn("peer-memory Ulysses exchange unavailable on some rank; using NCCL all_to_all")
             return None
-        return bufs
+        return self._buffers(n_loc, heads, device)        # a failure in here aborts the job (see _probe)
 
     def attend(self, ops, qkv, heads: int, out, ws):
         p, r = self.world, self.rank
@@ -145,6 +164,11 @@ class P2PUlyssesExchange(UlyssesExchange):
         ops.attention_scatter(recv[:n, :w], recv[:n, w:2 * w], recv[:n, 2 * w:], hl, out_ptrs, heads * 128, n_loc, r * w)
         h_out.barrier(channel=0)
         return aout
+
+
+def _host_id() -> str:
+    import socket
+    return socket.gethostname()
 
 
 _EXCHANGES = {}

@@ -59,9 +59,11 @@ class RMSNorm(nn.Module):
         self.weight = nn.Parameter(torch.ones(dim))
 
     def forward(self, x: Tensor) -> Tensor:
+        """norm(x.float()).to(dtype) * weight (wan_video_dit.py:106-111); x is NOT modified."""
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
-        ops.qk_rmsnorm_rope(x2, None, self.weight.to(x.dtype), None, self.eps)
-        return x2.view_as(x)
+        y = torch.empty_like(x2)
+        ops.qk_rmsnorm_rope(x2, None, self.weight.to(x.dtype), None, self.eps, q_out=y)
+        return y.view(x.shape)
 
 
 class AttentionModule(nn.Module):
@@ -114,15 +116,14 @@ class DiTBlock(nn.Module):
         self.gate = GateModule()
 
     def forward(self, x: Tensor, context: Tensor, t_mod: Tensor, freqs) -> Tensor:
-        """block(x, context, t_mod, freqs) -> x  (wan_video_dit.py:214-230).  ``freqs`` is an engine.RopeInfo
-        (built by model_fn / WanModel.rope_info); x (1, N, D) is NOT modified (the engine works on a copy)."""
-        if not isinstance(freqs, engine.RopeInfo):
-            raise TypeError("freqs must be an engine.RopeInfo (see WanModel.rope_info); complex freqs tensors are "
-                            "what the reference's eager rope_apply took")
+        """block(x, context, t_mod, freqs) -> x  (wan_video_dit.py:214-230).  ``freqs`` is the reference's complex
+        (N, 1, 64) tensor (wan_video_new.py:1392-1396) or an engine.RopeInfo (model_fn / WanModel.rope_info: the
+        device-resident table, no per-call gather); x (1, N, D) is NOT modified (the engine works on a copy)."""
         x2 = ops.as_2d(x).clone()
         ctx = ops.as_2d(context)
+        rope = engine.as_rope_info(freqs, x2.device)
         ws = engine.workspace(x2.shape[0], self.dim, self.ffn_dim, ctx.shape[0], x2.dtype, x2.device)
-        return engine.dit_block_forward(self, x2, ctx, t_mod, freqs, ws).view_as(x)
+        return engine.dit_block_forward(self, x2, ctx, t_mod, rope, ws).view_as(x)
 
 
 class Head(nn.Module):

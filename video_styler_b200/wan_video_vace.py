@@ -21,8 +21,26 @@ class VaceWanAttentionBlock(DiTBlock):
         self.after_proj = nn.Linear(dim, dim)
 
     def forward(self, c, x, context, t_mod, freqs):
-        raise NotImplementedError("VACE blocks are driven by VaceWanModel.forward (engine.vace_forward): the reference's "
-                                  "stacked-tensor protocol (wan_video_vace.py:13-24) is replaced by a preallocated hint buffer")
+        """The reference's stacked-tensor protocol (wan_video_vace.py:13-24) over the engine, for callers that drive
+        the blocks themselves: block 0 takes c (1, N, D) and returns stack([skip_0, c_1]); block k takes
+        stack([skip_0 .. skip_{k-1}, c_k]) and returns stack([skip_0 .. skip_k, c_{k+1}]).
+        ``VaceWanModel.forward`` does not go through here: it writes the hints once into a preallocated buffer."""
+        if self.block_id == 0:
+            c2 = ops.as_2d(c)
+            w, b = engine._lin(self.before_proj, c2.dtype, c2.device)
+            cur = ops.linear(c2.contiguous(), w, b, ops.EPI_BIAS_RES, residual=ops.as_2d(x).contiguous())   # before_proj(c) + x
+            skips = []
+        else:
+            skips = list(torch.unbind(c))
+            cur = ops.as_2d(skips.pop(-1)).clone()
+        ctx = ops.as_2d(context)
+        rope = engine.as_rope_info(freqs, cur.device)
+        ws = engine.workspace(cur.shape[0], self.dim, self.ffn_dim, ctx.shape[0], cur.dtype, cur.device)
+        engine.dit_block_forward(self, cur, ctx, t_mod, rope, ws)                     # DiTBlock.forward, in place on cur
+        w, b = engine._lin(self.after_proj, cur.dtype, cur.device)
+        skip = ops.linear(cur, w, b)                                                   # c_skip = after_proj(c)
+        like = skips[0] if skips else c
+        return torch.stack(skips + [skip.view(like.shape), cur.view(like.shape)])
 
 
 class VaceWanModel(nn.Module):
@@ -39,10 +57,10 @@ class VaceWanModel(nn.Module):
     def forward(self, x: Tensor, vace_context: Tensor, context: Tensor, t_mod: Tensor, freqs,
                 use_gradient_checkpointing: bool = False, use_gradient_checkpointing_offload: bool = False):
         """vace(x, vace_context, context, t_mod, freqs) -> tuple of (1, N, D) hints (wan_video_vace.py:53-87).
-        ``freqs`` is an engine.RopeInfo.  The hints are views of one workspace buffer (valid until the next call)."""
-        if not isinstance(freqs, engine.RopeInfo):
-            raise TypeError("freqs must be an engine.RopeInfo (see WanModel.rope_info)")
+        ``freqs`` is an engine.RopeInfo or the reference's complex (N, 1, 64) tensor.  The hints are views of one
+        workspace buffer (valid until the next call)."""
         x2, ctx = ops.as_2d(x), ops.as_2d(context)
+        freqs = engine.as_rope_info(freqs, x2.device)
         blk = self.vace_blocks[0]
         ws = engine.workspace(x2.shape[0], blk.dim, blk.ffn_dim, ctx.shape[0], x2.dtype, x2.device)
         hints = engine.vace_forward(self, x2, vace_context, ctx, t_mod, freqs, ws)
