@@ -114,6 +114,10 @@ def model_fn_wan_video(
     if use_unified_sequence_parallel:
         import torch.distributed as dist
         if dist.is_initialized() and dist.get_world_size(sp_group) > 1:
+            heads = dit.blocks[0].self_attn.num_heads
+            if heads % dist.get_world_size(sp_group) != 0:       # before any launch or collective: every rank raises alike
+                raise ValueError(f"Ulysses needs num_heads ({heads}) divisible by the sequence-parallel world size "
+                                 f"({dist.get_world_size(sp_group)})")
             exchange = make_exchange(sp_group, n_tokens, x.device)
             lo, hi, n_loc = shard_bounds(n_tokens, exchange.world, exchange.rank)
 
