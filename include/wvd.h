@@ -93,6 +93,24 @@ int wvd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
                   int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue, const void* gate,
                   const void* residual, int64_t ldr, wvd_stream_t stream);
 
+/* Three variants of the kernel sit behind it: WVD_GEMM_1CTA (128 x 256 tiles per CTA), WVD_GEMM_2CTA (256 x 256 tiles on
+ * CTA pairs, tcgen05.mma cta_group::2, two accumulator stages) and WVD_GEMM_2CTA_M512 (512 x 256 tiles on CTA pairs, the
+ * two halves filling all of TMEM: fewest operand bytes per flop).  WVD_GEMM_AUTO picks the one whose whole-wave unit
+ * count over the 148 SMs models fastest, and is what wvd_gemm_bf16 uses.  The selector is an argument (parity tests and
+ * the cuBLAS comparison run all of them on the same inputs); all variants accumulate in the same order and give
+ * bit-identical results.                                                                                            */
+enum { WVD_GEMM_AUTO = 0, WVD_GEMM_1CTA = 1, WVD_GEMM_2CTA = 2, WVD_GEMM_2CTA_M512 = 3 };
+int wvd_gemm_bf16_select(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
+                         int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue, const void* gate,
+                         const void* residual, int64_t ldr, int variant, wvd_stream_t stream);
+/* Grouped launch: C[:, g*N:(g+1)*N] = A . W[g]^T + bias[g] for g < groups (<= 3) in ONE launch -- the q | k | v
+ * projections of SelfAttention (wan_video_dit.py:131-133) share their input and write the column slices of one
+ * (M, 3N) buffer; A is read once per tile from L2 and the three problems fill the machine's waves together.
+ * W[g] are (N, K) row-major with the same ldw; bias may be NULL or hold NULL entries; N % 64 == 0 when groups > 1. */
+int wvd_gemm_bf16_grouped(const void* A, int64_t lda, const void* const* W, int64_t ldw, const void* const* bias,
+                          void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int groups, int variant,
+                          wvd_stream_t stream);
+
 /* ---- K8/K9: flash-style attention forward, head_dim 128, non-causal, no mask ---------------------------
  * out[s, h*128:(h+1)*128] = softmax(q_h k_h^T * scale) v_h ; q/k/v/out are (tokens, heads*128) bf16 views with
  * leading dims in elements.  Replaces flash_attention(): wan_video_dit.py:28-61 (self: sq == sk; cross: sk = 512). */

@@ -79,6 +79,13 @@ def linear(x, weight, bias=None, epilogue=EPI_BIAS, gate=None, residual=None, ou
     return _ret(y, out)
 
 
+def linear_grouped(x, weights, biases, out, variant=0):
+    n = weights[0].shape[0]
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        out[:, i * n:(i + 1) * n].copy_(F.linear(x, w, b))
+    return out
+
+
 def attention(q, k, v, num_heads, out=None, scale=None):
     y = O.attention(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), num_heads)[0]
     return _ret(y, out)

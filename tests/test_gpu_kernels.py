@@ -131,9 +131,15 @@ def _gemm_ref(x, w, b, epi, gate, res):
     return y
 
 
+@pytest.fixture(params=[_lib.GEMM_1CTA, _lib.GEMM_2CTA, _lib.GEMM_2CTA_M512], ids=["one_cta_tiles", "cta_pair_tiles", "cta_pair_m512_tiles"])
+def gemm_variant(request):
+    """Run the test on ALL GEMM variants (128 x 256 tiles per CTA; 256 x 256 and 512 x 256 tiles per CTA pair, cta_group::2)."""
+    return request.param
+
+
 @pytest.mark.parametrize("m,n,k", [(1, 8, 8), (72, 256, 256), (129, 264, 72), (200, 512, 320), (512, 1536, 1536),
-                                    (1280, 8960, 1536), (300, 1536, 8960), (520, 64, 512)])
-def test_gemm_bf16_all_epilogues(m, n, k):
+                                    (1280, 8960, 1536), (300, 1536, 8960), (520, 64, 512), (385, 520, 64)])
+def test_gemm_bf16_all_epilogues(m, n, k, gemm_variant):
     g = torch.Generator().manual_seed(m * 7 + n)
     x = torch.randn(m, k, generator=g).bfloat16()
     w = (torch.randn(n, k, generator=g) / math.sqrt(k)).bfloat16()
@@ -142,12 +148,39 @@ def test_gemm_bf16_all_epilogues(m, n, k):
     xd, wd, bd, gd, rd = (t.to(DEV) for t in (x, w, b, gate, res))
     for epi in (ops.EPI_BIAS, ops.EPI_BIAS_GELU, ops.EPI_BIAS_RES, ops.EPI_BIAS_GATE_RES):
         out = ops.linear(xd, wd, bd, epi, gd if epi == ops.EPI_BIAS_GATE_RES else None,
-                         rd if epi in (ops.EPI_BIAS_RES, ops.EPI_BIAS_GATE_RES) else None)
+                         rd if epi in (ops.EPI_BIAS_RES, ops.EPI_BIAS_GATE_RES) else None, variant=gemm_variant)
         _close(out, _gemm_ref(x, w, b, epi, gate, res), 5e-4, 1e-2)       # 1-ulp flips from fp32 summation order
-    _close(ops.linear(xd, wd), _gemm_ref(x, w, None, 0, None, None), 5e-4, 1e-2)          # no bias
+    _close(ops.linear(xd, wd, variant=gemm_variant), _gemm_ref(x, w, None, 0, None, None), 5e-4, 1e-2)          # no bias
     r2 = rd.clone()                                                                      # in-place residual stream
-    ops.linear(xd, wd, bd, ops.EPI_BIAS_GATE_RES, gd, r2, out=r2)
+    ops.linear(xd, wd, bd, ops.EPI_BIAS_GATE_RES, gd, r2, out=r2, variant=gemm_variant)
     _close(r2, _gemm_ref(x, w, b, ops.EPI_BIAS_GATE_RES, gate, res), 5e-4, 1e-2)
+    # output into a column slice of a wider buffer (the q|k|v layout): neighbours untouched (TMA store clipping)
+    wide = torch.full((m, n + 16), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.linear(xd, wd, bd, out=wide[:, 8:8 + n], variant=gemm_variant)
+    _close(wide[:, 8:8 + n], _gemm_ref(x, w, b, 0, None, None), 5e-4, 1e-2)
+    assert float((wide[:, :8] - 7).abs().max()) == 0 and float((wide[:, 8 + n:] - 7).abs().max()) == 0
+    _no_timeouts()
+
+
+@pytest.mark.parametrize("m,n,k,g", [(300, 256, 512, 3), (1000, 1536, 1536, 3), (129, 320, 72, 2), (3705, 5120, 512, 3)])
+def test_gemm_grouped_equals_separate_launches(m, n, k, g, gemm_variant):
+    """The grouped q|k|v launch (one A, up to three weights, column slices of one output) is bit-identical to the
+    separate launches and matches F.linear."""
+    gen = torch.Generator().manual_seed(m + n + g)
+    x = torch.randn(m, k, generator=gen).bfloat16().to(DEV)
+    ws = [(torch.randn(n, k, generator=gen) / math.sqrt(k)).bfloat16().to(DEV) for _ in range(g)]
+    bs = [(torch.randn(n, generator=gen) * 0.1).bfloat16().to(DEV) for _ in range(g)]
+    out = torch.full((m, g * n + 8), 3.0, dtype=torch.bfloat16, device=DEV)
+    ops.linear_grouped(x, ws, bs, out=out[:, :g * n], variant=gemm_variant)
+    for i in range(g):
+        sep = ops.linear(x, ws[i], bs[i], variant=gemm_variant)
+        assert torch.equal(out[:, i * n:(i + 1) * n], sep), i
+        _close(sep, _gemm_ref(x.cpu(), ws[i].cpu(), bs[i].cpu(), 0, None, None), 5e-4, 1e-2)
+    assert float((out[:, g * n:] - 3).abs().max()) == 0
+    # a missing bias in one group
+    ops.linear_grouped(x, ws, [bs[0]] + [None] * (g - 1), out=out[:, :g * n], variant=gemm_variant)
+    assert torch.equal(out[:, (g - 1) * n:g * n], ops.linear(x, ws[g - 1], None, variant=gemm_variant))
+    _no_timeouts()
     _no_timeouts()
 
 
@@ -164,18 +197,19 @@ def test_gemm_exact_on_integers_and_strided_output():
     _no_timeouts()
 
 
-def test_gemm_linearity_at_full_c3_shape():
+def test_gemm_linearity_at_full_c3_shape(gemm_variant):
     """Size-independent property at the BASELINE shape (29,640 x 5120 x 5120): W(2x) = 2 W(x) exactly in bf16
     (scaling by 2 is exact), and W(x) on a row subset equals the subset of W(x)."""
     m, n, k = 29640, 5120, 5120
     g = torch.Generator(device=DEV).manual_seed(1)
     x = torch.randn(m, k, device=DEV, generator=g).bfloat16()
     w = (torch.randn(n, k, device=DEV, generator=g) / math.sqrt(k)).bfloat16()
-    y = ops.linear(x, w)
-    y2 = ops.linear(x * 2, w)
+    y = ops.linear(x, w, variant=gemm_variant)
+    y2 = ops.linear(x * 2, w, variant=gemm_variant)
     assert torch.equal(y2, y * 2)
+    assert torch.equal(y, ops.linear(x, w, variant=gemm_variant % 3 + 1))      # all variants accumulate in the same order
     rows = torch.tensor([0, 127, 128, 14820, 29567, 29568, 29639], device=DEV)
-    ysub = ops.linear(x[rows].contiguous(), w)
+    ysub = ops.linear(x[rows].contiguous(), w, variant=gemm_variant)
     assert torch.equal(ysub, y[rows])
     ref = F.linear(x[rows].float(), w.float()).bfloat16()
     _close(ysub, ref, 5e-4, 5e-3)

@@ -25,6 +25,10 @@ SIGNATURES = {
     "wvd_gate_residual": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
     "wvd_gemm_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                       c_int, c_void_p, c_void_p, c_int64, c_void_p],
+    "wvd_gemm_bf16_select": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                             c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "wvd_gemm_bf16_grouped": [c_void_p, c_int64, ctypes.POINTER(c_void_p), c_int64, ctypes.POINTER(c_void_p), c_void_p,
+                              c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p],
     "wvd_gemm_f32": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                      c_int, c_void_p, c_void_p, c_int64, c_void_p],
     "wvd_attention_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64,
@@ -44,6 +48,7 @@ MAX_PEERS = 8
 WVD_BF16, WVD_F32 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_GATE_RES = 0, 1, 2, 3
 ATTN_AUTO, ATTN_TWO_TILE, ATTN_PAIR = 0, 1, 2
+GEMM_AUTO, GEMM_1CTA, GEMM_2CTA, GEMM_2CTA_M512 = 0, 1, 2, 3
 
 _lib = None
 

@@ -157,9 +157,8 @@ def dit_block_forward(block, x: Tensor, context: Tensor, t_mod: Tensor, rope: Ro
     # ---- self attention: x += gate_msa * o(attn(rope(rms(q)), rope(rms(k)), v)) ----
     h = ops.ln_modulate(x, mod[0], mod[1], eps=eps, out=ws.get("h", (n, d)))
     qkv = ws.get("qkv", (n, 3 * d))
-    for i, proj in enumerate((sa.q, sa.k, sa.v)):
-        w, b = _lin(proj, dt, dev)
-        ops.linear(h, w, b, out=qkv[:, i * d:(i + 1) * d])
+    wb = [_lin(proj, dt, dev) for proj in (sa.q, sa.k, sa.v)]
+    ops.linear_grouped(h, [w for w, _ in wb], [b for _, b in wb], out=qkv)        # one launch for q | k | v
     ops.qk_rmsnorm_rope(qkv[:, :d], qkv[:, d:2 * d], _norm_w(sa.norm_q, dt, dev), _norm_w(sa.norm_k, dt, dev),
                         _unwrap(sa.norm_q).eps, rope.table, rope.grid, rope.token_offset, rope.frame_ids)
     a = exchange.attend(ops, qkv, heads, ws.get("attn", (n, d)), ws)

@@ -147,8 +147,10 @@ def qk_rmsnorm_rope(q: Tensor, k: Optional[Tensor], wq: Tensor, wk: Optional[Ten
 
 
 def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, epilogue: int = EPI_BIAS,
-           gate: Optional[Tensor] = None, residual: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
-    """out = epilogue(x @ weight.T + bias) -- F.linear with fused GELU-tanh / residual / gate*y + residual."""
+           gate: Optional[Tensor] = None, residual: Optional[Tensor] = None, out: Optional[Tensor] = None,
+           variant: int = _lib.GEMM_AUTO) -> Tensor:
+    """out = epilogue(x @ weight.T + bias) -- F.linear with fused GELU-tanh / residual / gate*y + residual.
+    ``variant`` names the 1-CTA or the CTA-pair kernel explicitly (tests, tools); the default picks by tile-wave model."""
     x = _chk2d(x, "x")
     weight = _chk2d(weight, "weight")
     m, k = x.shape
@@ -166,12 +168,44 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, epilogue: i
         residual = _chk2d(residual, "residual")
         if residual.shape != (m, n) or residual.dtype != x.dtype:
             raise WvdError("linear: residual shape/dtype mismatch")
-    fn = _lib.load().wvd_gemm_bf16 if x.dtype == torch.bfloat16 else _lib.load().wvd_gemm_f32
     _dt(x)
     if m == 0:
         return out
-    check(fn(x.data_ptr(), _ld(x), weight.data_ptr(), _ld(weight), _p(bias), out.data_ptr(), _ld(out), m, n, k, epilogue,
-             _p(gate), _p(residual), _ld(residual) if residual is not None else 0, _stream()), "wvd_gemm")
+    args = (x.data_ptr(), _ld(x), weight.data_ptr(), _ld(weight), _p(bias), out.data_ptr(), _ld(out), m, n, k, epilogue,
+            _p(gate), _p(residual), _ld(residual) if residual is not None else 0)
+    if x.dtype != torch.bfloat16:
+        check(_lib.load().wvd_gemm_f32(*args, _stream()), "wvd_gemm_f32")
+    elif variant == _lib.GEMM_AUTO:
+        check(_lib.load().wvd_gemm_bf16(*args, _stream()), "wvd_gemm_bf16")
+    else:
+        check(_lib.load().wvd_gemm_bf16_select(*args, variant, _stream()), "wvd_gemm_bf16_select")
+    return out
+
+
+def linear_grouped(x: Tensor, weights, biases, out: Tensor, variant: int = _lib.GEMM_AUTO) -> Tensor:
+    """out[:, g*N:(g+1)*N] = x @ weights[g].T + biases[g] for up to 3 same-shape weights in ONE launch (the q | k | v
+    projections, wan_video_dit.py:131-133).  fp32 parity mode, or shapes the grouped kernel does not take, run the
+    projections one by one through ``linear`` (same kernels, same results)."""
+    x = _chk2d(x, "x")
+    out = _chk2d(out, "out")
+    g = len(weights)
+    m, k = x.shape
+    n = weights[0].shape[0]
+    if out.shape != (m, g * n):
+        raise WvdError(f"linear_grouped: out has shape {tuple(out.shape)}, expected {(m, g * n)}")
+    same = all(_chk2d(w, "weight").shape == (n, k) and w.dtype == x.dtype and _ld(w) == _ld(weights[0]) for w in weights)
+    if x.dtype != torch.bfloat16 or not same or g > 3 or n % 64 != 0:
+        for i, (w, b) in enumerate(zip(weights, biases)):
+            linear(x, w, b, out=out[:, i * n:(i + 1) * n], variant=variant)
+        return out
+    biases = [_vec(b, n, "bias", x) for b in biases]
+    if m == 0:
+        return out
+    import ctypes
+    wp = (ctypes.c_void_p * 3)(*[w.data_ptr() for w in weights])
+    bp = (ctypes.c_void_p * 3)(*[(b.data_ptr() if b is not None else None) for b in biases])
+    check(_lib.load().wvd_gemm_bf16_grouped(x.data_ptr(), _ld(x), wp, _ld(weights[0]), bp, out.data_ptr(), _ld(out), m, n, k,
+                                            g, variant, _stream()), "wvd_gemm_bf16_grouped")
     return out
 
 
