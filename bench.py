@@ -261,6 +261,7 @@ def main():
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers (the JSON line is then marked invalid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the torch-eager (cuBLAS + SDPA / FA2) leg")
+    ap.add_argument("--no-loop", action="store_true", help="skip the CFG-step (denoise loop) timing, plain vs fused")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the untimed sharded-vs-unsharded check")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -359,6 +360,50 @@ def main():
         for _ in range(1):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
+        # the default CFG denoising step (posi + nega velocity, CFG combine, Euler update: wan_video_new.py:526-540) both
+        # ways: the plain loop as the reference runs it, and with the loop-level fusion of SURVEY section 8(f)1 (text
+        # embedding + cross-attention K/V cached across steps and branches, CFG + Euler as one device kernel, each velocity
+        # prediction replayed as a CUDA graph).  Same outputs (tests/test_gpu_model.py); FLOPs per step still 2 x the full count.
+        loop = None
+        if not args.no_loop:
+            nega = torch.zeros_like(devin["context"])
+            lat0 = devin["latents"].clone()
+
+            def cfg_steps(n, **kw):
+                return V.denoise(dit, vace, lat0, devin["context"], nega, vace_context=devin.get("vace_context"), vace_scale=1.0,
+                                 num_inference_steps=n, cfg_scale=5.0, use_unified_sequence_parallel=usp, **kw)
+            loop = {}
+            for name, kw in (("plain", dict(cache_text=False, fused_step=False, use_cuda_graph=False)),
+                             ("fused", dict(cache_text=True, fused_step=True, use_cuda_graph=not usp))):
+                n_steps = 3
+                if name == "fused":
+                    cache = V.TextCache()
+                    gfn = V.GraphedModelFn(dit=dit, vace=vace, vace_scale=1.0, use_unified_sequence_parallel=usp, text_cache=cache) if not usp else None
+                    sch = V.FlowMatchScheduler(shift=5, sigma_min=0.0, extra_one_step=True)
+                    sch.set_timesteps(50, shift=5.0)
+
+                    def run_fused(n):
+                        lat = lat0
+                        for i in range(n):
+                            ts_i = sch.timesteps[i].unsqueeze(0).to(dtype=torch.bfloat16, device=dev)
+                            if gfn is not None:
+                                vp = gfn(lat, ts_i, devin["context"], devin.get("vace_context")).clone()
+                                vn = gfn(lat, ts_i, nega, devin.get("vace_context"))
+                            else:
+                                vp = V.model_fn_wan_video(dit=dit, vace=vace, latents=lat, timestep=ts_i, context=devin["context"], vace_context=devin.get("vace_context"), vace_scale=1.0, use_unified_sequence_parallel=usp, text_cache=cache)
+                                vn = V.model_fn_wan_video(dit=dit, vace=vace, latents=lat, timestep=ts_i, context=nega, vace_context=devin.get("vace_context"), vace_scale=1.0, use_unified_sequence_parallel=usp, text_cache=cache)
+                            lat = ops.cfg_euler_step(lat, vp, vn, 5.0, sch.dsigma(sch.timesteps[i]))
+                        return lat
+                    run_fused(1)                                    # capture / fill the caches outside the timed region
+                    loop[name + "_s_per_cfg_step"] = timed(lambda: run_fused(n_steps), 1) / 1e3 / n_steps
+                else:
+                    cfg_steps(1, **kw)
+                    loop[name + "_s_per_cfg_step"] = timed(lambda: cfg_steps(n_steps, **kw), 1) / 1e3 / n_steps
+            loop["speedup"] = loop["plain_s_per_cfg_step"] / loop["fused_s_per_cfg_step"]
+            loop["what"] = ("one default CFG denoising step = 2 velocity predictions + CFG combine + Euler update, 3 steps timed; "
+                            "plain = the reference's loop on the wvd kernels; fused = text embedding + cross-attention K/V cached per "
+                            "prompt, CFG + Euler in one kernel" + ("" if usp else ", CUDA-graph replay of each prediction") +
+                            "; bit-identical outputs")
         gpu_ref = gpu_c1 = None
         if world == 1 and not args.no_gpu_reference:
             gpu_ref = gpu_reference_leg(dit, vace, devin, t_dev, step_resident(), ms, wl["size"])
@@ -411,6 +456,8 @@ def main():
             line["invalid"] = f"debug run with {args.layers} layers"
         if parity is not None:
             line["parity"] = parity
+        if loop is not None:
+            line["denoise_loop"] = loop
         if gpu_ref is not None:
             line["gpu_reference"] = gpu_ref
         if world == 1 and not args.no_cpu_baseline:

@@ -81,6 +81,12 @@ int wvd_qk_rmsnorm_rope(const void* q, int64_t ldq, const void* k, int64_t ldk, 
  * out = x + y * scale   (VACE hint injection, diffsynth/pipelines/wan_video_new.py:1445-1450)            */
 int wvd_scale_add(const void* x, const void* y, float scale, void* out, int64_t n_elems, int dtype,
                   wvd_stream_t stream);
+/* One pass for the tail of a denoising step: CFG combine (diffsynth/pipelines/wan_video_new.py:535) and the Euler
+ * update of FlowMatchScheduler.step (diffsynth/schedulers/flow_match.py:72-82):
+ *   out = x + (v_nega + cfg_scale * (v_posi - v_nega)) * dsigma,  every operation rounded to the tensor dtype like the
+ * reference's eager expressions.  v_nega == NULL (cfg_scale == 1): out = x + v_posi * dsigma.  out may alias x.     */
+int wvd_cfg_euler_step(const void* x, const void* v_posi, const void* v_nega, float cfg_scale, float dsigma, void* out,
+                       int64_t n_elems, int dtype, wvd_stream_t stream);
 /* out = x + gate[c] * y (GateModule, wan_video_dit.py:189-194) -- only used when the producer is not a GEMM */
 int wvd_gate_residual(const void* x, const void* gate, const void* y, void* out, int64_t n_tokens, int dim,
                       int dtype, wvd_stream_t stream);
@@ -117,11 +123,13 @@ int wvd_gemm_bf16_grouped(const void* A, int64_t lda, const void* const* W, int6
 int wvd_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                       void* out, int64_t ldo, int num_heads, int64_t sq, int64_t sk, int head_dim, float scale,
                       wvd_stream_t stream);
-/* Two kernels sit behind it: WVD_ATTN_TWO_TILE (two Q tiles per CTA; the 512-key text cross-attention) and
- * WVD_ATTN_PAIR (2-CTA clusters sharing K/V, triple-buffered S in TMEM; long self-attention).  WVD_ATTN_AUTO picks by
- * key length (PAIR for sk >= 2048) and is what wvd_attention_fwd uses.  The selector is an ARGUMENT -- the library
- * keeps no mutable dispatch state -- so that the parity tests can run both kernels on the same inputs.            */
-enum { WVD_ATTN_AUTO = 0, WVD_ATTN_TWO_TILE = 1, WVD_ATTN_PAIR = 2 };
+/* Three kernels sit behind it: WVD_ATTN_TWO_TILE (two Q tiles per CTA; the 512-key text cross-attention),
+ * WVD_ATTN_CG2 (2-CTA clusters, one tcgen05.mma cta_group::2 stream with M = 256 over the pair, K/V split over the pair,
+ * triple-buffered S in TMEM; long self-attention) and WVD_ATTN_PAIR (its cta_group::1 predecessor: K/V multicast to both
+ * CTAs; kept for A/B).  WVD_ATTN_AUTO picks by key length (CG2 for sk >= 2048) and is what wvd_attention_fwd uses.  The
+ * selector is an ARGUMENT -- the library keeps no mutable dispatch state -- so that the parity tests can run all kernels
+ * on the same inputs.                                                                                              */
+enum { WVD_ATTN_AUTO = 0, WVD_ATTN_TWO_TILE = 1, WVD_ATTN_PAIR = 2, WVD_ATTN_CG2 = 3 };
 int wvd_attention_fwd_select(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                              void* out, int64_t ldo, int num_heads, int64_t sq, int64_t sk, int head_dim, float scale,
                              int which, wvd_stream_t stream);

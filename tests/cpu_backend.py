@@ -95,6 +95,11 @@ def scale_add(x, y, scale, out=None):
     return _ret(x + y * scale, out)
 
 
+def cfg_euler_step(x, v_posi, v_nega, cfg_scale, dsigma, out=None):
+    v = v_posi if v_nega is None else v_nega + cfg_scale * (v_posi - v_nega)
+    return _ret(x + v * dsigma, out)
+
+
 def gate_residual(x, gate, y, out=None):
     return _ret(x + gate * y, out)
 

@@ -247,6 +247,36 @@ def test_denoise_loop_on_gpu_matches_oracle():
     assert _lib.debug_flags()["timeouts"] == 0
 
 
+def test_loop_fusion_switches_are_bit_identical_on_gpu():
+    """Section 8(f)1: text-embedding + cross-attention K/V cache, CFG-combine + Euler step as one device kernel, CUDA-graph
+    replay of each velocity prediction -- every switch of denoise() must give the SAME bits as the plain loop."""
+    cfg, vcfg = O.DIT_CONFIGS["tiny"], O.VACE_CONFIGS["tiny"]
+    sd = {k: v.to(DEV).bfloat16() for k, v in O.make_state_dict(O.dit_param_shapes(cfg), seed=0, perturb_norms=True).items()}
+    vsd = {k: v.to(DEV).bfloat16() for k, v in O.make_state_dict(O.vace_param_shapes(vcfg), seed=3, perturb_norms=True).items()}
+    dit, vace = V.WanModel(has_image_input=False, **cfg), V.VaceWanModel(has_image_input=False, **vcfg)
+    dit.load_state_dict(sd, strict=True, assign=True)
+    vace.load_state_dict(vsd, strict=True, assign=True)
+    dit.requires_grad_(False), vace.requires_grad_(False)
+    inp = {k: v.to(DEV).bfloat16() for k, v in O.make_inputs((1, 16, 3, 8, 12), cfg["text_dim"], seed=1, with_vace=True).items()}
+    nega = torch.zeros_like(inp["context"])
+
+    def run(**kw):
+        return V.denoise(dit, vace, inp["latents"], inp["context"], nega, vace_context=inp["vace_context"], vace_scale=1.0,
+                         num_inference_steps=3, cfg_scale=5.0, torch_dtype=torch.bfloat16, **kw)
+    plain = run(cache_text=False, fused_step=False, use_cuda_graph=False)
+    assert torch.equal(run(cache_text=True, fused_step=False), plain)
+    assert torch.equal(run(cache_text=False, fused_step=True), plain)
+    assert torch.equal(run(cache_text=True, fused_step=True, use_cuda_graph=True), plain)
+    # the fused step against the eager expressions, bf16 and fp32, with and without CFG
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for dt in (torch.bfloat16, torch.float32):
+        x, vp, vn = (torch.randn(1, 16, 3, 8, 16, device=DEV, generator=g).to(dt) for _ in range(3))
+        ds = -0.01234567
+        assert torch.equal(ops.cfg_euler_step(x, vp, vn, 5.0, ds), x + (vn + 5.0 * (vp - vn)) * ds)
+        assert torch.equal(ops.cfg_euler_step(x, vp, None, 1.0, ds), x + vp * ds)
+    assert _lib.debug_flags()["timeouts"] == 0
+
+
 class _Wrapped(torch.nn.Module):
     """Stand-in for diffsynth.vram_management.AutoWrappedModule (layers.py:36-60): the real module sits in ``.module``
     and the wrapper itself has no ``weight`` (the reference is not on the GPU box; tests/test_install_reference.py

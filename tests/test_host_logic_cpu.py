@@ -204,3 +204,52 @@ def test_block_with_reference_complex_freqs_and_padded_rope_rows(golden_dir):
     out, _ = cpu_backend.qk_rmsnorm_rope(q.clone(), None, w, None, 1e-6, tab, (3, 4, 6), 0)
     ref, _ = cpu_backend.qk_rmsnorm_rope(q[:72].clone(), None, w, None, 1e-6, tab, (3, 4, 6), 0)
     assert torch.equal(out[:72], ref) and torch.isfinite(out).all()
+
+
+def test_text_cache_is_bit_identical_and_invalidates(golden_dir):
+    """engine.TextCache (text embedding + cross-attention K/V once per prompt): same bits as the uncached call, a hit on
+    the second call, a miss when the context tensor is modified in place or a cross-attention weight changes."""
+    fix = _load(golden_dir, "tiny_vace_lora")
+    dit, vace = build_models(fix)
+    base = run_model_fn(fix, dit, vace, cpu_backend)
+    cfg = O.DIT_CONFIGS["tiny"]
+    inp = O.make_inputs(fix["latent_shape"], cfg["text_dim"], seed=1, with_vace=True)
+    cache = V.TextCache()
+    ts = torch.tensor([fix["timestep"]])
+
+    def call(ctx):
+        with torch.no_grad():
+            return V.model_fn_wan_video(dit=dit, vace=vace, latents=inp["latents"], timestep=ts, context=ctx,
+                                        vace_context=inp["vace_context"], vace_scale=1.0, ops=cpu_backend, text_cache=cache)
+    ctx = inp["context"].clone()
+    a, b = call(ctx), call(ctx)
+    assert torch.equal(a, base) and torch.equal(b, base) and (cache.hits, cache.misses) == (1, 1)
+    n_kv = len(cache.entry(ctx)["kv"])
+    assert n_kv == len(dit.blocks) + len(vace.vace_blocks)
+    ctx.mul_(0.5)                                              # in-place edit: version counter moves -> recomputed
+    c = call(ctx)
+    assert not torch.equal(c, base) and cache.misses == 2
+    with torch.no_grad():
+        dit.blocks[1].cross_attn.k.weight.add_(0.01)           # e.g. a LoRA merged after the first call
+        want = V.model_fn_wan_video(dit=dit, vace=vace, latents=inp["latents"], timestep=ts, context=ctx,
+                                    vace_context=inp["vace_context"], vace_scale=1.0, ops=cpu_backend)
+    assert torch.equal(call(ctx), want)
+
+
+def test_denoise_switches_are_bit_identical():
+    """denoise(cache_text / fused_step on or off) gives the same latents (CPU stand-in kernels; the fused step itself is
+    checked against the eager expressions on the GPU)."""
+    f = dict(size="tiny", seeds=dict(dit=0, vace=3, lora=2, inputs=1), perturb=True, weight_scale=1.0, with_vace=False, lora=False)
+    dit, _ = build_models(f)
+    inp = O.make_inputs((1, 16, 3, 8, 12), O.DIT_CONFIGS["tiny"]["text_dim"], seed=1)
+    nega = torch.zeros_like(inp["context"])
+    import functools
+    import video_styler_b200.pipeline as P
+    orig = P.model_fn_wan_video
+    P.model_fn_wan_video = functools.partial(orig, ops=cpu_backend)
+    try:
+        outs = [V.denoise(dit, None, inp["latents"], inp["context"], nega, num_inference_steps=2, cfg_scale=5.0,
+                          torch_dtype=torch.float32, cache_text=c) for c in (False, True)]
+    finally:
+        P.model_fn_wan_video = orig
+    assert torch.equal(outs[0], outs[1])

@@ -40,7 +40,7 @@ def test_install_on_real_reference_modules_with_vram_wrappers(golden_dir):
     assert type(vace.vace_blocks[0].norm1).__name__ == "AutoWrappedModule"
     pipe = types.SimpleNamespace(model_fn=w.model_fn_wan_video, dit=dit, vace=vace)
     V.install(pipe)
-    assert pipe.model_fn is V.model_fn_wan_video
+    assert pipe.model_fn.func is V.model_fn_wan_video and isinstance(pipe.wvd_text_cache, V.TextCache)
     inp = O.make_inputs(fix["latent_shape"], cfg["text_dim"], seed=1, with_vace=True)
     fn = functools.partial(pipe.model_fn, ops=cpu_backend)
     with torch.no_grad():
@@ -49,6 +49,11 @@ def test_install_on_real_reference_modules_with_vram_wrappers(golden_dir):
                  tea_cache=None, use_unified_sequence_parallel=False, motion_bucket_id=None, cfg_merge=False)
     m = O.parity_metrics(out, fix["output"])
     assert m["max_abs"] <= 5e-5 and m["rel_l2"] <= 2e-5, m
+    # second call with the same context object: text embedding + cross K/V come from the cache, same bits
+    with torch.no_grad():
+        out2 = fn(dit=pipe.dit, vace=pipe.vace, latents=inp["latents"], timestep=torch.tensor([fix["timestep"]]),
+                  context=inp["context"], vace_context=inp["vace_context"], vace_scale=1.0)
+    assert torch.equal(out, out2) and pipe.wvd_text_cache.hits == 1 and pipe.wvd_text_cache.misses == 1
 
 
 def test_lora_loader_equals_the_real_general_lora_loader():

@@ -1,57 +1,66 @@
-"""Developer tool: A/B timing of several builds of libwvd (tools/build_attn_variants.sh) on the c3 self-attention shape,
-interleaved in one process so that all variants see the same thermal / power state.  Also times torch SDPA (cuDNN).
+"""Sustained A/B of the self-attention kernels at the c3 shape (29,640 tokens, 40 heads) under the power cap: each
+contender runs back to back for --secs seconds in rotating order (tools/gemm_sustained.py explains why).  cuDNN / flash
+SDPA (torch F.scaled_dot_product_attention) runs beside them."""
+import argparse
+import os
+import sys
+import time
 
-    python tools/attn_ab.py [variant ...]        # names under video_styler_b200/variants/, default: all + the main lib
-"""
-import ctypes, glob, os, statistics, sys
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-from video_styler_b200 import _lib
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from video_styler_b200 import _lib, ops  # noqa: E402
 
-n, h = int(os.environ.get("N", 29640)), int(os.environ.get("H", 40))
-reps, inner = int(os.environ.get("REPS", 5)), int(os.environ.get("INNER", 20))
-names = sys.argv[1:] or [os.path.basename(p)[len("libwvd_"):-3] for p in sorted(glob.glob(os.path.join(ROOT, "video_styler_b200/variants/libwvd_*.so")))]
-libs = {"main": ctypes.CDLL(_lib.LIB_PATH)}
-for nm in names:
-    libs[nm] = ctypes.CDLL(os.path.join(ROOT, "video_styler_b200/variants", f"libwvd_{nm}.so"))
-for lib in libs.values():
-    lib.wvd_attention_fwd.restype = ctypes.c_int
-    lib.wvd_attention_fwd.argtypes = _lib.SIGNATURES["wvd_attention_fwd"]
-
+ap = argparse.ArgumentParser()
+ap.add_argument("--secs", type=float, default=0.7)
+ap.add_argument("--rounds", type=int, default=2)
+ap.add_argument("--tokens", type=int, default=29640)
+ap.add_argument("--heads", type=int, default=40)
+ap.add_argument("--out", default="gpurun_out/attn_ab.txt")
+ap.add_argument("--lib", default=None, help="developer: another build of libwvd.so (e.g. a -D variant)")
+a = ap.parse_args()
+if a.lib:
+    _lib.LIB_PATH = os.path.abspath(a.lib)
+DEV = "cuda"
+n, h = a.tokens, a.heads
 d = h * 128
-qkv = torch.randn(n, 3 * d, device="cuda").bfloat16()
-out = torch.empty(n, d, device="cuda", dtype=torch.bfloat16)
+g = torch.Generator(device=DEV).manual_seed(0)
+qkv = torch.randn(n, 3 * d, device=DEV, generator=g).bfloat16()
+out = torch.empty(n, d, device=DEV, dtype=torch.bfloat16)
 q4 = qkv[:, :d].reshape(1, n, h, 128).transpose(1, 2)
 k4 = qkv[:, d:2 * d].reshape(1, n, h, 128).transpose(1, 2)
 v4 = qkv[:, 2 * d:].reshape(1, n, h, 128).transpose(1, 2)
-stream = torch.cuda.current_stream().cuda_stream
-
-
-def run(lib):
-    rc = lib.wvd_attention_fwd(qkv.data_ptr(), 3 * d, qkv.data_ptr() + 2 * d, 3 * d, qkv.data_ptr() + 4 * d, 3 * d,
-                               out.data_ptr(), d, h, n, n, 128, 128 ** -0.5, stream)
-    assert rc == 0
-
-
-fns = {nm: (lambda lib=lib: run(lib)) for nm, lib in libs.items()}
-fns["sdpa"] = lambda: F.scaled_dot_product_attention(q4, k4, v4)
-ref = None
-times = {nm: [] for nm in fns}
-for r in range(reps + 1):
-    for nm, fn in fns.items():
+cont = [("sdpa", lambda: F.scaled_dot_product_attention(q4, k4, v4)),
+        ("wvd-pair(cg1)", lambda: ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h, out=out, kernel=_lib.ATTN_PAIR)),
+        ("wvd-cg2", lambda: ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h, out=out, kernel=_lib.ATTN_CG2))]
+fl = 4.0 * n * n * d
+ref = F.scaled_dot_product_attention(q4, k4, v4).transpose(1, 2).reshape(n, d)
+lines = []
+for nm, fn in cont[1:]:
+    fn(); torch.cuda.synchronize()
+    rel = float((out.float() - ref.float()).norm() / ref.float().norm())
+    lines.append(f"# {nm}: rel_l2 vs SDPA {rel:.2e}")
+res = {nm: [] for nm, _ in cont}
+for r in range(a.rounds):
+    order = cont[r % len(cont):] + cont[:r % len(cont)]
+    for nm, fn in order:
+        fn(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        fn()
+        t0 = time.perf_counter()
         e0.record()
-        for _ in range(inner):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        if r > 0:
-            times[nm].append(e0.elapsed_time(e1) / inner)
-flops = 4.0 * n * n * 128 * h
-for nm, t in times.items():
-    med = statistics.median(t)
-    print(f"{nm:12s} median {med:7.3f} ms  min {min(t):7.3f}  max {max(t):7.3f}   {flops / med / 1e9:7.0f} TFLOP/s")
+        cnt = 0
+        while time.perf_counter() - t0 < a.secs:
+            for _ in range(5):
+                fn()
+            cnt += 5
+            torch.cuda.synchronize()
+        e1.record(); torch.cuda.synchronize()
+        res[nm].append(e0.elapsed_time(e1) / cnt)
+lines.append(f"# sustained ms per launch ({n} tokens, {h} heads; {a.secs} s per contender, rotating order) and TFLOP/s")
+for nm, vs in res.items():
+    lines.append("  %-16s %s ms   %s TFLOP/s" % (nm, " / ".join("%.3f" % v for v in vs), " / ".join("%.0f" % (fl / (v * 1e-3) / 1e12) for v in vs)))
+print("\n".join(lines))
+print("flags", _lib.debug_flags())
+os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
+open(a.out, "w").write("\n".join(lines) + "\n")

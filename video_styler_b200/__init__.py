@@ -7,7 +7,8 @@ library of hand-written CUDA kernels (include/wvd.h).  Public surface mirrors th
 """
 from ._lib import WvdError  # noqa: F401
 from .lora import GeneralLoRALoader, load_lora  # noqa: F401
-from .pipeline import FlowMatchScheduler, denoise, install, model_fn_wan_video  # noqa: F401
+from .engine import TextCache  # noqa: F401
+from .pipeline import FlowMatchScheduler, GraphedModelFn, denoise, install, model_fn_wan_video  # noqa: F401
 from .wan_video_dit import WanModel  # noqa: F401
 from .wan_video_vace import VaceWanModel  # noqa: F401
 

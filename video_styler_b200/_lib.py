@@ -22,6 +22,7 @@ SIGNATURES = {
                             c_int64, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
                             c_int, c_void_p],
     "wvd_scale_add": [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p],
+    "wvd_cfg_euler_step": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_int64, c_int, c_void_p],
     "wvd_gate_residual": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
     "wvd_gemm_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                       c_int, c_void_p, c_void_p, c_int64, c_void_p],
@@ -47,7 +48,7 @@ MAX_PEERS = 8
 
 WVD_BF16, WVD_F32 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_GATE_RES = 0, 1, 2, 3
-ATTN_AUTO, ATTN_TWO_TILE, ATTN_PAIR = 0, 1, 2
+ATTN_AUTO, ATTN_TWO_TILE, ATTN_PAIR, ATTN_CG2 = 0, 1, 2, 3
 GEMM_AUTO, GEMM_1CTA, GEMM_2CTA, GEMM_2CTA_M512 = 0, 1, 2, 3
 
 _lib = None

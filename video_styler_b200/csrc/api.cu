@@ -114,6 +114,7 @@ bool first_use_on_current_device(unsigned long long* flag_word) {
 int gemm_read_diag(unsigned long long* out);
 int attn_read_diag(unsigned long long* out);
 int attn_pair_read_diag(unsigned long long* out);
+int attn_cg2_read_diag(unsigned long long* out);
 
 }  // namespace wvd
 
@@ -134,7 +135,10 @@ extern "C" __attribute__((visibility("default"))) int wvd_debug_flags(unsigned l
     unsigned long long a[8] = {0}, b[8] = {0}, c[8] = {0};
     if (gemm_read_diag(a) != 0 || attn_read_diag(b) != 0 || attn_pair_read_diag(c) != 0)
         return set_error(WVD_ERR_CUDA, "reading diagnostics failed");
-    if (c[0] != 0) { b[0] += c[0]; b[1] = c[1]; b[2] = c[2]; b[3] = c[3]; }      // both attention kernels report as "attn"
+    if (c[0] != 0) { b[0] += c[0]; b[1] = c[1]; b[2] = c[2]; b[3] = c[3]; }      // all attention kernels report as "attn"
+    unsigned long long d[8] = {0};
+    if (attn_cg2_read_diag(d) != 0) return set_error(WVD_ERR_CUDA, "reading diagnostics failed");
+    if (d[0] != 0) { b[0] += d[0]; b[1] = d[1]; b[2] = d[2]; b[3] = d[3]; }
     for (int i = 0; i < 8; ++i) out[i] = a[i];
     out[0] = a[0] + b[0];
     if (b[0] != 0) { out[1] = b[1]; out[2] = b[2]; out[3] = b[3]; }

@@ -361,6 +361,35 @@ scale_add_kernel(const T* __restrict__ x, const T* __restrict__ y, float scale, 
     }
 }
 
+// CFG combine + Euler step of the denoising loop in one pass (wan_video_new.py:535,540; flow_match.py:72-82), with the
+// rounding points of the reference's tensor-dtype expressions:
+//   noise = v_nega + cfg * (v_posi - v_nega)        (each operation rounded to the tensor dtype; skipped if v_nega == NULL)
+//   out   = x + noise * dsigma                      (product rounded, then the sum)
+template <typename T>
+__global__ void __launch_bounds__(256)
+cfg_euler_kernel(const T* __restrict__ x, const T* __restrict__ vp, const T* __restrict__ vn, float cfg, float dsigma,
+                 T* __restrict__ out, long long nvec) {
+    using IO = VecIO<T>;
+    constexpr int VE = IO::N;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float a[VE], p[VE], n[VE];
+        IO::load(x + i * VE, a);
+        IO::load(vp + i * VE, p);
+        if (vn != nullptr) {
+            IO::load(vn + i * VE, n);
+#pragma unroll
+            for (int e = 0; e < VE; ++e) {
+                const float d = IO::rnd(__fsub_rn(p[e], n[e]));
+                p[e] = IO::rnd(__fadd_rn(n[e], IO::rnd(__fmul_rn(cfg, d))));
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < VE; ++e) a[e] = __fadd_rn(a[e], IO::rnd(__fmul_rn(p[e], dsigma)));
+        IO::store(out + i * VE, a);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 gate_residual_kernel(const T* __restrict__ x, const T* __restrict__ gate, const T* __restrict__ y, T* __restrict__ out,
@@ -546,6 +575,24 @@ extern "C" __attribute__((visibility("default"))) int wvd_scale_add(const void* 
         ew::scale_add_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, scale, (__nv_bfloat16*)out, nvec);
     else
         ew::scale_add_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)y, scale, (float*)out, nvec);
+    WVD_CHECK_CUDA(cudaGetLastError());
+    return WVD_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_cfg_euler_step(const void* x, const void* v_posi, const void* v_nega, float cfg_scale,
+                                  float dsigma, void* out, int64_t n_elems, int dtype, wvd_stream_t stream) {
+    WVD_REQUIRE(dtype == WVD_BF16 || dtype == WVD_F32, "wvd_cfg_euler_step: bad dtype %d", dtype);
+    if (n_elems == 0) return WVD_OK;
+    WVD_REQUIRE(x && v_posi && out && n_elems > 0, "wvd_cfg_euler_step: null pointer");
+    const int ve = dtype == WVD_BF16 ? 8 : 4;
+    WVD_REQUIRE(n_elems % ve == 0, "wvd_cfg_euler_step: n_elems must be a multiple of %d", ve);
+    WVD_REQUIRE(aligned16(x) && aligned16(v_posi) && aligned16(v_nega) && aligned16(out), "wvd_cfg_euler_step: pointers must be 16-byte aligned");
+    const long long nvec = n_elems / ve;
+    const unsigned grid = ew::stream_grid(nvec, 256);
+    if (dtype == WVD_BF16)
+        ew::cfg_euler_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)v_posi, (const __nv_bfloat16*)v_nega, cfg_scale, dsigma, (__nv_bfloat16*)out, nvec);
+    else
+        ew::cfg_euler_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)v_posi, (const float*)v_nega, cfg_scale, dsigma, (float*)out, nvec);
     WVD_CHECK_CUDA(cudaGetLastError());
     return WVD_OK;
 }

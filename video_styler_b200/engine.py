@@ -129,6 +129,41 @@ def as_rope_info(freqs, device, ops=_cuda_ops) -> RopeInfo:
     raise TypeError("freqs must be an engine.RopeInfo (WanModel.rope_info) or the reference's complex (N, 1, 64) tensor")
 
 
+class TextCache:
+    """Text-side work that is constant across the denoising loop, computed once per prompt instead of once per call:
+    ``dit.text_embedding(context)`` (wan_video_new.py:1357) and every block's cross-attention K = norm_k(k(ctx)),
+    V = v(ctx) (wan_video_dit.py:177-179) -- the reference recomputes them 100x per video (50 steps x posi / nega).
+    They depend only on ``context`` and the weights, so outputs are bit-identical with and without the cache.
+
+    Keyed by the context tensor OBJECT (held weakly) and its in-place version counter; entries are validated against
+    the data pointer / version of the weights they were computed from, so a LoRA merge or ``load_state_dict`` after
+    the fact simply misses.  Memory: 2 x (L_ctx x D) per block and prompt (0.5 GB per prompt for the 14B + VACE model)."""
+
+    def __init__(self, max_prompts: int = 4):
+        self.max_prompts = max_prompts
+        self._entries = {}          # id(context) -> dict(ref, version, emb, kv={id(block): (kc, vc, stamp)})
+        self.hits = self.misses = 0
+
+    def clear(self):
+        self._entries.clear()
+
+    def entry(self, context: Tensor):
+        import weakref
+        e = self._entries.get(id(context))
+        if e is not None and (e["ref"]() is not context or e["version"] != context._version):
+            e = None
+        if e is None:
+            if len(self._entries) >= self.max_prompts:
+                self._entries.pop(next(iter(self._entries)))
+            e = dict(ref=weakref.ref(context), version=context._version, emb=None, emb_stamp=None, kv={})
+            self._entries[id(context)] = e
+        return e
+
+    @staticmethod
+    def stamp(*params):
+        return tuple((p.data_ptr(), p._version) for p in params)
+
+
 class SelfAttnExchange:
     """Single-GPU: attention reads q|k|v in place.  ulysses.UlyssesExchange overrides this with the all-to-all."""
     world = 1
@@ -142,10 +177,11 @@ _LOCAL = SelfAttnExchange()
 
 
 def dit_block_forward(block, x: Tensor, context: Tensor, t_mod: Tensor, rope: RopeInfo, ws: Workspace,
-                      ops=_cuda_ops, exchange: SelfAttnExchange = _LOCAL) -> Tensor:
+                      ops=_cuda_ops, exchange: SelfAttnExchange = _LOCAL, text_entry: Optional[dict] = None) -> Tensor:
     """DiTBlock.forward (wan_video_dit.py:214-230) on a (tokens, D) residual stream, updated IN PLACE.
 
-    context: (L_ctx, D) text embedding (already through dit.text_embedding)."""
+    context: (L_ctx, D) text embedding (already through dit.text_embedding).  text_entry: a TextCache entry of this
+    prompt -- the block's cross-attention K / V are then computed once and reused by every later call."""
     dt, dev = x.dtype, x.device
     n, d = x.shape
     sa, ca = block.self_attn, block.cross_attn
@@ -172,11 +208,23 @@ def dit_block_forward(block, x: Tensor, context: Tensor, t_mod: Tensor, rope: Ro
     q = ops.linear(h, w, b, out=ws.get("qc", (n, d)))
     ops.qk_rmsnorm_rope(q, None, _norm_w(ca.norm_q, dt, dev), None, _unwrap(ca.norm_q).eps)
     lc = context.shape[0]
-    w, b = _lin(ca.k, dt, dev)
-    kc = ops.linear(context, w, b, out=ws.get("kc", (lc, d)))
-    ops.qk_rmsnorm_rope(kc, None, _norm_w(ca.norm_k, dt, dev), None, _unwrap(ca.norm_k).eps)
-    w, b = _lin(ca.v, dt, dev)
-    vc = ops.linear(context, w, b, out=ws.get("vc", (lc, d)))
+    cached = None
+    if text_entry is not None:
+        stamp = TextCache.stamp(_unwrap(ca.k).weight, _unwrap(ca.v).weight, _unwrap(ca.norm_k).weight)
+        cached = text_entry["kv"].get(id(block))
+        if cached is not None and cached[2] != stamp:
+            cached = None
+    if cached is not None:
+        kc, vc = cached[0], cached[1]
+    else:
+        own = text_entry is not None                     # cached K / V live in their own buffers, not in the workspace
+        w, b = _lin(ca.k, dt, dev)
+        kc = ops.linear(context, w, b, out=torch.empty((lc, d), dtype=dt, device=dev) if own else ws.get("kc", (lc, d)))
+        ops.qk_rmsnorm_rope(kc, None, _norm_w(ca.norm_k, dt, dev), None, _unwrap(ca.norm_k).eps)
+        w, b = _lin(ca.v, dt, dev)
+        vc = ops.linear(context, w, b, out=torch.empty((lc, d), dtype=dt, device=dev) if own else ws.get("vc", (lc, d)))
+        if own:
+            text_entry["kv"][id(block)] = (kc, vc, stamp)
     a = ops.attention(q, kc, vc, heads, out=ws.get("attn", (n, d)))
     w, b = _lin(ca.o, dt, dev)
     ops.linear(a, w, b, ops.EPI_BIAS_RES, residual=x, out=x)
@@ -203,7 +251,7 @@ def head_forward(head, x: Tensor, t: Tensor, ws: Workspace, ops=_cuda_ops) -> Te
 
 def vace_forward(vace, x: Tensor, vace_context: Tensor, context: Tensor, t_mod: Tensor, rope: RopeInfo,
                  ws: Workspace, ops=_cuda_ops, exchange: SelfAttnExchange = _LOCAL,
-                 token_slice: Optional[slice] = None) -> Tensor:
+                 token_slice: Optional[slice] = None, text_entry: Optional[dict] = None) -> Tensor:
     """VaceWanModel.forward + VaceWanAttentionBlock.forward (wan_video_vace.py:13-24, 53-87).
 
     Returns the hints as ONE preallocated (n_hints, tokens, D) buffer (the reference's O(k^2) stack/unbind copying
@@ -229,7 +277,7 @@ def vace_forward(vace, x: Tensor, vace_context: Tensor, context: Tensor, t_mod: 
             w, b = _lin(blk.before_proj, dt, dev)
             c_new = ops.linear(c_buf, w, b, ops.EPI_BIAS_RES, residual=x, out=ws.get("vace_c2", (n, d)))
             c_buf = c_new
-        dit_block_forward(blk, c_buf, context, t_mod, rope, ws, ops, exchange)
+        dit_block_forward(blk, c_buf, context, t_mod, rope, ws, ops, exchange, text_entry)
         w, b = _lin(blk.after_proj, dt, dev)
         ops.linear(c_buf, w, b, out=hints[j])
     return hints

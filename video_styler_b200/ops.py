@@ -258,6 +258,21 @@ def scale_add(x: Tensor, y: Tensor, scale: float, out: Optional[Tensor] = None) 
     return out
 
 
+def cfg_euler_step(x: Tensor, v_posi: Tensor, v_nega: Optional[Tensor], cfg_scale: float, dsigma: float,
+                   out: Optional[Tensor] = None) -> Tensor:
+    """x + (v_nega + cfg_scale * (v_posi - v_nega)) * dsigma in one pass, with the reference's per-operation rounding
+    (wan_video_new.py:535,540; flow_match.py:72-82).  v_nega None: x + v_posi * dsigma."""
+    ts = [t for t in (x, v_posi, v_nega) if t is not None]
+    if any((not t.is_cuda) or t.shape != x.shape or t.dtype != x.dtype or not t.is_contiguous() for t in ts):
+        raise WvdError("cfg_euler_step: contiguous CUDA tensors of equal shape/dtype expected")
+    out = torch.empty_like(x) if out is None else out
+    if x.numel() == 0:
+        return out
+    check(_lib.load().wvd_cfg_euler_step(x.data_ptr(), v_posi.data_ptr(), _p(v_nega), float(cfg_scale), float(dsigma),
+                                         out.data_ptr(), x.numel(), _dt(x), _stream()), "wvd_cfg_euler_step")
+    return out
+
+
 def gate_residual(x: Tensor, gate: Tensor, y: Tensor, out: Optional[Tensor] = None) -> Tensor:
     """x + gate*y (GateModule, wan_video_dit.py:189-194)."""
     x, y = _chk2d(x, "x"), _chk2d(y, "y")

@@ -68,14 +68,17 @@ def model_fn_wan_video(
     fuse_vae_embedding_in_latents: bool = False,
     rope_indices: Optional[Tensor] = None,
     sp_group=None,
+    text_cache: Optional[engine.TextCache] = None,
     ops=_cuda_ops,
     **kwargs,
 ) -> Tensor:
     """One velocity prediction (B,16,F,H,W) -> (B,16,F,H,W); keyword-compatible with the reference model_fn.
 
     Extra keywords: ``rope_indices`` (the fixed WanModel.forward variant, wan_video_dit.py:378-384), ``sp_group``
-    (torch.distributed group for Ulysses; default group when ``use_unified_sequence_parallel``), ``ops`` (kernel
-    backend; tests inject a CPU restatement to exercise the host logic -- the product default is libwvd.so)."""
+    (torch.distributed group for Ulysses; default group when ``use_unified_sequence_parallel``), ``text_cache`` (an
+    engine.TextCache: text embedding and cross-attention K / V computed once per prompt instead of once per call --
+    identical outputs; off unless given), ``ops`` (kernel backend; tests inject a CPU restatement to exercise the host
+    logic -- the product default is libwvd.so)."""
     for name, val in (("audio_embeds", audio_embeds), ("clip_feature", clip_feature), ("y", y),
                       ("reference_latents", reference_latents), ("pose_latents", pose_latents),
                       ("face_pixel_values", face_pixel_values), ("control_camera_latents_input", control_camera_latents_input),
@@ -93,7 +96,20 @@ def model_fn_wan_video(
     t_mod = dit.time_projection(t).unflatten(1, (6, dit.dim))
     if motion_bucket_id is not None and motion_controller is not None:
         t_mod = t_mod + motion_controller(motion_bucket_id).unflatten(1, (6, dit.dim))
-    context = dit.text_embedding(context)
+    text_entry = None
+    if text_cache is not None:
+        text_entry = text_cache.entry(context)
+        te = dit.text_embedding
+        stamp = engine.TextCache.stamp(*[p_ for p_ in te.parameters()])
+        if text_entry["emb"] is None or text_entry["emb_stamp"] != stamp:
+            text_entry["emb"], text_entry["emb_stamp"] = te(context), stamp
+            text_entry["kv"].clear()
+            text_cache.misses += 1
+        else:
+            text_cache.hits += 1
+        context = text_entry["emb"]
+    else:
+        context = dit.text_embedding(context)
 
     x = latents
     if x.shape[0] != context.shape[0]:                       # merged CFG (:1361-1364)
@@ -139,12 +155,13 @@ def model_fn_wan_video(
         if vace_context is not None:
             vc = vace_context[b:b + 1] if vace_context.shape[0] == bsz else vace_context
             hints = engine.vace_forward(vace, xb, vc, ctx, tm, rope, ws, ops, exchange,
-                                        token_slice=slice(lo, hi) if exchange.world > 1 else None)
+                                        token_slice=slice(lo, hi) if exchange.world > 1 else None,
+                                        text_entry=_sample_entry(text_entry, b, bsz))
         if tea_cache_update:
             xb = ops.as_2d(tea_cache.update(xb.unsqueeze(0)))
         else:
             for block_id, block in enumerate(dit.blocks):
-                engine.dit_block_forward(block, xb, ctx, tm, rope, ws, ops, exchange)
+                engine.dit_block_forward(block, xb, ctx, tm, rope, ws, ops, exchange, _sample_entry(text_entry, b, bsz))
                 if hints is not None and block_id in vace.vace_layers_mapping:
                     ops.scale_add(xb, hints[vace.vace_layers_mapping[block_id]], float(vace_scale), out=xb)
             if tea_cache is not None:
@@ -157,6 +174,17 @@ def model_fn_wan_video(
         outs.append(y_all.clone())
     out = torch.stack(outs, dim=0)
     return dit.unpatchify(out, (f, h, w))
+
+
+def _sample_entry(text_entry, b: int, bsz: int):
+    """Per-sample view of a TextCache entry: a merged-CFG call (batch 2: posi | nega contexts in one tensor) keeps one
+    K / V set per sample."""
+    if text_entry is None:
+        return None
+    if bsz == 1:
+        return text_entry
+    sub = text_entry.setdefault("samples", {})
+    return sub.setdefault(b, dict(kv={}))
 
 
 def _ffn_dim(dit) -> int:
@@ -190,40 +218,101 @@ class FlowMatchScheduler:
         ts = torch.as_tensor(timestep).detach().float().cpu()
         return int(torch.argmin((self.timesteps - ts).abs()))
 
-    def step(self, model_output: Tensor, timestep, sample: Tensor, to_final: bool = False, **_) -> Tensor:
+    def dsigma(self, timestep, to_final: bool = False) -> float:
+        """sigma_next - sigma of the step at ``timestep``, evaluated in fp32 like flow_match.py:76-81 does."""
         i = self._index(timestep)
-        sigma = float(self.sigmas[i])
-        sigma_next = 0.0 if (to_final or i + 1 >= len(self.timesteps)) else float(self.sigmas[i + 1])
-        return sample + model_output * (sigma_next - sigma)
+        nxt = torch.zeros((), dtype=self.sigmas.dtype) if (to_final or i + 1 >= len(self.timesteps)) else self.sigmas[i + 1]
+        return float(nxt - self.sigmas[i])
+
+    def step(self, model_output: Tensor, timestep, sample: Tensor, to_final: bool = False, **_) -> Tensor:
+        return sample + model_output * self.dsigma(timestep, to_final)
 
     def add_noise(self, original_samples: Tensor, noise: Tensor, timestep) -> Tensor:
         sigma = float(self.sigmas[self._index(timestep)])
         return (1 - sigma) * original_samples + sigma * noise
 
 
+class GraphedModelFn:
+    """One velocity prediction as a replayed CUDA graph: the ~900 kernel launches of a call (C-ABI kernels and the few
+    PyTorch ones alike) are captured once per (shapes, prompt, flags) and replayed with no host work in between.
+    Inputs are copied into static buffers; the output buffer is reused by the next replay (clone it to keep it).
+    The TextCache, if any, is filled by the warm-up call, so the captured graph reads the cached K / V.
+    What the graph buys is launch latency: nothing at c3 on one GPU (1.5 s of long kernels), the gaps between the short
+    kernels of a 3,705-token rank at 8 GPUs or of the 1,280-token c1 model."""
+
+    def __init__(self, **fixed):
+        self.fixed = fixed            # dit, vace, vace_scale, use_unified_sequence_parallel, text_cache ...
+        self._graphs = {}
+
+    def __call__(self, latents: Tensor, timestep: Tensor, context: Tensor, vace_context: Optional[Tensor] = None) -> Tensor:
+        key = (tuple(latents.shape), latents.dtype, id(context), context._version,
+               None if vace_context is None else tuple(vace_context.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            st = dict(latents=latents.clone(), timestep=timestep.clone(), context=context,
+                      vace_context=None if vace_context is None else vace_context.clone())
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                       # warm-up off the capture: workspaces, tensor maps, caches
+                for _ in range(2):
+                    model_fn_wan_video(**self.fixed, **st)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = model_fn_wan_video(**self.fixed, **st)
+            g = self._graphs[key] = (graph, st, out)
+        graph, st, out = g
+        st["latents"].copy_(latents)
+        st["timestep"].copy_(timestep)
+        if vace_context is not None and vace_context.data_ptr() != st["vace_context"].data_ptr():
+            st["vace_context"].copy_(vace_context)
+        graph.replay()
+        return out
+
+
 @torch.no_grad()
 def denoise(dit, vace, latents: Tensor, context_posi: Tensor, context_nega: Optional[Tensor] = None,
             vace_context: Optional[Tensor] = None, vace_scale: float = 1.0, num_inference_steps: int = 50,
             cfg_scale: float = 5.0, sigma_shift: float = 5.0, torch_dtype=torch.bfloat16, progress=None,
-            use_unified_sequence_parallel: bool = False, scheduler: Optional[FlowMatchScheduler] = None) -> Tensor:
+            use_unified_sequence_parallel: bool = False, scheduler: Optional[FlowMatchScheduler] = None,
+            cache_text: bool = True, use_cuda_graph: bool = False, fused_step: bool = True) -> Tensor:
     """The denoising loop of WanVideoPipeline.__call__ (wan_video_new.py:515-542): per step the timestep is rounded
-    to the model dtype (:526), posi (+ nega) velocity, CFG combine (:535), Euler step (:540)."""
+    to the model dtype (:526), posi (+ nega) velocity, CFG combine (:535), Euler step (:540).
+
+    Loop-level fusion on top of the per-call kernels, all switchable and all bit-identical to the plain loop:
+    cache_text      text embedding + cross-attention K / V once per prompt (engine.TextCache) instead of 100x per video
+    fused_step      CFG combine + Euler update as ONE kernel on the device (wvd_cfg_euler_step); sigma pairs are looked
+                    up on the host from the step index, so there is no per-step .cpu() sync (flow_match.py:73-75)
+    use_cuda_graph  each velocity prediction replayed as a CUDA graph (GraphedModelFn)"""
     sch = scheduler or FlowMatchScheduler(shift=5, sigma_min=0.0, extra_one_step=True)
     sch.set_timesteps(num_inference_steps, shift=sigma_shift)
     it = sch.timesteps if progress is None else progress(sch.timesteps)
+    fixed = dict(dit=dit, vace=vace, vace_scale=vace_scale, use_unified_sequence_parallel=use_unified_sequence_parallel)
+    if cache_text:
+        fixed["text_cache"] = engine.TextCache()
+    on_gpu = latents.is_cuda
+    call = GraphedModelFn(**fixed) if (use_cuda_graph and on_gpu) else (
+        lambda latents, timestep, context, vace_context=None: model_fn_wan_video(latents=latents, timestep=timestep, context=context,
+                                                                               vace_context=vace_context, **fixed))
     for i, ts in enumerate(it):
         timestep = ts.unsqueeze(0).to(dtype=torch_dtype, device=latents.device)
-        common = dict(dit=dit, vace=vace, latents=latents, timestep=timestep, vace_context=vace_context,
-                      vace_scale=vace_scale, use_unified_sequence_parallel=use_unified_sequence_parallel)
-        v = model_fn_wan_video(context=context_posi, **common)
+        v = call(latents, timestep, context_posi, vace_context)
+        vn = None
         if cfg_scale != 1.0:
-            vn = model_fn_wan_video(context=context_nega, **common)
-            v = vn + cfg_scale * (v - vn)
-        latents = sch.step(v, sch.timesteps[i], latents)
+            if use_cuda_graph and on_gpu:
+                v = v.clone()                                  # the graph's output buffer is shared between replays of one graph only,
+            vn = call(latents, timestep, context_nega, vace_context)      # but posi / nega are different graphs: the clone is for safety
+        if fused_step and on_gpu and latents.is_contiguous():
+            latents = _cuda_ops.cfg_euler_step(latents, v.contiguous(), None if vn is None else vn.contiguous(), cfg_scale,
+                                               sch.dsigma(sch.timesteps[i]))
+        else:
+            if vn is not None:
+                v = vn + cfg_scale * (v - vn)
+            latents = sch.step(v, sch.timesteps[i], latents)
     return latents
 
 
-def install(pipe, use_usp: bool = False):
+def install(pipe, use_usp: bool = False, cache_text: bool = True):
     """Plug the B200 path into a reference ``WanVideoPipeline`` (diffsynth/pipelines/wan_video_new.py):
 
         pipe = WanVideoPipeline.from_pretrained(...); pipe.load_lora(pipe.vace, ...); pipe.enable_vram_management()
@@ -232,9 +321,14 @@ def install(pipe, use_usp: bool = False):
     ``pipe.model_fn`` is the instance attribute every caller goes through (:529,534 denoise loop; :117 training_loss).
     The module tree, state-dict keys, merged LoRA weights and vram wrappers are left untouched."""
     import functools
-    fn = model_fn_wan_video
+    extra = {}
     if use_usp:
-        fn = functools.partial(model_fn_wan_video, use_unified_sequence_parallel=True)
+        extra["use_unified_sequence_parallel"] = True
+    if cache_text:
+        # the pipeline passes the same posi / nega context tensors at every step (wan_video_new.py:529,534): their text
+        # embedding and cross-attention K / V are computed once per prompt instead of 100x per video
+        pipe.wvd_text_cache = extra["text_cache"] = engine.TextCache()
+    fn = functools.partial(model_fn_wan_video, **extra) if extra else model_fn_wan_video
     pipe.model_fn = fn
     pipe.use_unified_sequence_parallel = bool(use_usp) or getattr(pipe, "use_unified_sequence_parallel", False)
     return pipe
