@@ -163,6 +163,16 @@ int wvd_ulysses_unpack_out(const void* recv, void* out, int64_t ldo, int64_t n_l
  *                 into out_ptrs[t / rows_per_peer] at local row t % rows_per_peer, columns
  *                 [col_offset, col_offset + num_heads*128) of a (rows_per_peer, ldo) buffer -- the o-projection input. */
 #define WVD_MAX_PEERS 8
+/*   qk_rmsnorm_rope_scatter : wvd_qk_rmsnorm_rope (bf16, RoPE on) whose STORES are the q / k part of scatter_qkv: the
+ *                 finished vector of head h goes straight to recv_ptrs[h / (heads/P)], slot q (0) or k (1) of row
+ *                 rank*n_local + row -- no pack / scatter pass over q and k ("K3 writing straight into the send
+ *                 layout"); scatter_v then moves only the v third of the buffer.                                        */
+int wvd_qk_rmsnorm_rope_scatter(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* wq, const void* wk,
+                                void* const* recv_ptrs, int64_t n_local, int dim, int head_dim, float eps,
+                                const void* rope_cs, const int32_t* frame_ids, int grid_f, int grid_h, int grid_w,
+                                int64_t token_offset, int world, int rank, wvd_stream_t stream);
+int wvd_ulysses_scatter_v(const void* qkv, int64_t ld, void* const* recv_ptrs, int64_t n_local, int heads, int head_dim,
+                          int world, int rank, wvd_stream_t stream);
 int wvd_ulysses_scatter_qkv(const void* qkv, int64_t ld, void* const* recv_ptrs, int64_t n_local, int heads,
                             int head_dim, int world, int rank, wvd_stream_t stream);
 int wvd_attention_fwd_scatter(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

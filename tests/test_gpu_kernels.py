@@ -332,6 +332,26 @@ def test_ulysses_peer_scatter_kernels_match_the_collective_layouts(world, heads,
     for d in range(world):
         want = torch.stack([packed[src][d] for src in range(world)]).reshape(world * n_loc, 3 * w)   # all_to_all_single
         assert torch.equal(recv[d].cpu(), want)
+    # the same receive buffers filled by the RoPE kernel's fused stores (q, k) + the v-only scatter: bit-identical to
+    # RMSNorm+RoPE in place followed by the full scatter
+    table = ops.make_rope_table(O.rope_tables_3d(128), DEV)
+    grid = (world, n_loc // 4 + 1, 4)                                   # any grid with >= world * n_loc - pad tokens
+    wq = (1 + 0.1 * torch.randn(heads * 128, generator=g)).bfloat16().to(DEV)
+    wk = (1 + 0.1 * torch.randn(heads * 128, generator=g)).bfloat16().to(DEV)
+    recv_a = [torch.zeros_like(t) for t in recv]
+    recv_b = [torch.zeros_like(t) for t in recv]
+    d_ = heads * 128
+    for r in range(world):
+        buf = qkv[r].to(DEV)
+        ops.qk_rmsnorm_rope_scatter(buf[:, :d_], buf[:, d_:2 * d_], wq, wk, 1e-6, table, grid, r * n_loc, None,
+                                    [t.data_ptr() for t in recv_b], r)
+        ops.ulysses_scatter_v(buf, heads, [t.data_ptr() for t in recv_b], r)
+        assert torch.equal(buf.cpu(), qkv[r])                           # q, k left untouched
+        ops.qk_rmsnorm_rope(buf[:, :d_], buf[:, d_:2 * d_], wq, wk, 1e-6, table, grid, r * n_loc)
+        ops.ulysses_scatter_qkv(buf, heads, [t.data_ptr() for t in recv_a], r)
+    torch.cuda.synchronize()
+    for d in range(world):
+        assert torch.equal(recv_a[d], recv_b[d]), d
     # return trip: the last shard is padded by `pad` rows; every rank attends its heads over all real tokens (the
     # 2,197- and 2,400-token cases take the long-sequence CTA-pair kernel's scatter epilogue)
     n = world * n_loc - pad

@@ -41,6 +41,9 @@ SIGNATURES = {
     "wvd_ulysses_pack_qkv": [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
     "wvd_ulysses_unpack_out": [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p],
     "wvd_ulysses_scatter_qkv": [c_void_p, c_int64, ctypes.POINTER(c_void_p), c_int64, c_int, c_int, c_int, c_int, c_void_p],
+    "wvd_ulysses_scatter_v": [c_void_p, c_int64, ctypes.POINTER(c_void_p), c_int64, c_int, c_int, c_int, c_int, c_void_p],
+    "wvd_qk_rmsnorm_rope_scatter": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int64,
+                                    c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_void_p],
     "wvd_attention_fwd_scatter": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, ctypes.POINTER(c_void_p), c_int64,
                                   c_int64, c_int64, c_int, c_int, c_int64, c_int64, c_int, c_float, c_int, c_void_p],
 }

@@ -217,8 +217,10 @@ int launch_ln(const void* x, int64_t ldx, const void* shift, const void* scale, 
 // ------------------------------------------------------------------------------------------------
 // RMSNorm(q), RMSNorm(k) over the full hidden dim, * weight, then 3-D RoPE on adjacent channel pairs
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MAXV, bool ROPE>
-__device__ __forceinline__ void rms_rope_row(const T* __restrict__ xr, const T* __restrict__ w, T* __restrict__ orow,
+// `dst(vi)` = where vector vi (channels [vi*VE, vi*VE + VE)) of the finished row goes: the row itself, or -- Ulysses,
+// fused exchange -- the receive buffer of the rank that owns the vector's head (a peer pointer: the store travels NVLink)
+template <typename T, int MAXV, bool ROPE, typename Dst>
+__device__ __forceinline__ void rms_rope_row(const T* __restrict__ xr, const T* __restrict__ w, Dst dst,
                                              int dim, float eps, int lane, const float2* cs /*[VE/2]*/) {
     using IO = VecIO<T>;
     constexpr int VE = IO::N;
@@ -275,10 +277,12 @@ __device__ __forceinline__ void rms_rope_row(const T* __restrict__ xr, const T* 
                     o[2 * pr + 1] = re * cs[pr].y + im * cs[pr].x;
                 }
             }
-            IO::store(orow + vi * VE, o);
+            IO::store(dst(vi), o);
         }
     }
 }
+
+struct PeerPtrs { uint4* p[WVD_MAX_PEERS]; };
 
 // blockIdx.y selects the tensor (0 = q, 1 = k): q and k rows are independent, one warp each.
 template <typename T, int MAXV, bool ROPE>
@@ -320,8 +324,59 @@ qk_rmsnorm_rope_kernel(const T* __restrict__ q, long long ldq, const T* __restri
             }
         }
     }
-    if (blockIdx.y == 0) rms_rope_row<T, MAXV, ROPE>(q + row * ldq, wq, qo + row * ldqo, dim, eps, lane, cs);
-    else rms_rope_row<T, MAXV, ROPE>(k + row * ldk, wk, ko + row * ldko, dim, eps, lane, cs);
+    if (blockIdx.y == 0) {
+        T* orow = qo + row * ldqo;
+        rms_rope_row<T, MAXV, ROPE>(q + row * ldq, wq, [orow](int vi) { return orow + vi * VE; }, dim, eps, lane, cs);
+    } else {
+        T* orow = ko + row * ldko;
+        rms_rope_row<T, MAXV, ROPE>(k + row * ldk, wk, [orow](int vi) { return orow + vi * VE; }, dim, eps, lane, cs);
+    }
+}
+
+// The same kernel with the Ulysses all-to-all of q and k FUSED into its stores (bf16, RoPE on): the finished vector of
+// head h goes straight into the receive buffer of rank h / heads_local, at
+//   recv[dest][(rank * n_local + row)][which][h % heads_local][channel % 128]      (which: 0 = q, 1 = k; v is slot 2)
+// -- the layout the attention kernel reads in place (see ulysses_scatter_kernel).  No separate pack / scatter pass for q, k.
+template <int MAXV>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (MAXV <= 20 ? 2 : 1))
+qk_rmsnorm_rope_scatter_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ k,
+                               long long ldk, const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
+                               PeerPtrs recv, long long n_local, int dim, float eps, const float2* __restrict__ rope_cs,
+                               const int* __restrict__ frame_ids, int gf, int gh, int gw, long long token_offset,
+                               int heads_local, int rank) {
+    using T = __nv_bfloat16;
+    constexpr int VE = 8;
+    const int lane = threadIdx.x & 31;
+    const long long row = static_cast<long long>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (row >= n_local) return;
+    float2 cs[VE / 2];
+    {
+        const int pair0 = ((lane * VE) % 128) / 2;
+        const long long n = token_offset + row;
+        const int pw = static_cast<int>(n % gw);
+        const int ph = static_cast<int>((n / gw) % gh);
+        int pf = min(static_cast<int>(n / (static_cast<long long>(gw) * gh)), gf - 1);      // pad rows of the last shard
+        if (frame_ids != nullptr) pf = frame_ids[pf];
+#pragma unroll
+        for (int pr = 0; pr < VE / 2; ++pr) {
+            const int j = pair0 + pr;
+            int axis, jj, pos;
+            if (j < 22) { axis = 0; jj = j; pos = pf; }
+            else if (j < 43) { axis = 1; jj = j - 22; pos = ph; }
+            else { axis = 2; jj = j - 43; pos = pw; }
+            cs[pr] = __ldg(rope_cs + (static_cast<long long>(axis) * 1024 + pos) * 32 + jj);
+        }
+    }
+    const int which = blockIdx.y;
+    const long long per_row = 3ll * heads_local * 16;                   // 16-byte vectors per receive-buffer row
+    const long long row_base = (static_cast<long long>(rank) * n_local + row) * per_row + static_cast<long long>(which) * heads_local * 16;
+    auto dst = [&](int vi) {
+        const int head = vi >> 4;                                       // 16 vectors of 8 channels per 128-channel head
+        const int dest = head / heads_local;
+        return reinterpret_cast<T*>(recv.p[dest] + row_base + (head - dest * heads_local) * 16 + (vi & 15));
+    };
+    if (which == 0) rms_rope_row<T, MAXV, true>(q + row * ldq, wq, dst, dim, eps, lane, cs);
+    else rms_rope_row<T, MAXV, true>(k + row * ldk, wk, dst, dim, eps, lane, cs);
 }
 
 template <typename T, int MAXV>
@@ -437,19 +492,20 @@ ulysses_pack_kernel(const uint4* __restrict__ qkv, long long ld_vec, uint4* __re
 // Fused pack + all-to-all: the same gather as ulysses_pack_kernel, but each destination's chunk is stored straight into
 // THAT rank's receive buffer over NVLink (peer pointers from a symmetric-memory rendezvous), in the layout the attention
 // kernel reads: recv_dest[(rank*n_local + row)][which][hl][c].  1,280-byte contiguous runs per (dest,row,which) at P = 8.
-struct PeerPtrs { uint4* p[WVD_MAX_PEERS]; };
+// which0: first of the three tensors to move (0 = q, k and v; 2 = v only, when q and k were scattered by the RoPE kernel)
 __global__ void __launch_bounds__(256)
 ulysses_scatter_kernel(const uint4* __restrict__ qkv, long long ld_vec, PeerPtrs recv, long long n_local, int heads,
-                       int hd_vec, int world, int rank) {
+                       int hd_vec, int world, int rank, int which0) {
     const int hl_n = heads / world;
-    const long long per_row = 3ll * hl_n * hd_vec;                  // vectors per (dest,row)
-    const long long total = static_cast<long long>(world) * n_local * per_row;
+    const int nw = 3 - which0;
+    const long long per_row = 3ll * hl_n * hd_vec;                  // vectors per (dest,row) in the receive buffer
+    const long long total = static_cast<long long>(world) * n_local * nw * hl_n * hd_vec;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int c = static_cast<int>(i % hd_vec);
         long long t = i / hd_vec;
         const int hl = static_cast<int>(t % hl_n); t /= hl_n;
-        const int which = static_cast<int>(t % 3); t /= 3;
+        const int which = which0 + static_cast<int>(t % nw); t /= nw;
         const long long row = t % n_local;
         const int dest = static_cast<int>(t / n_local);
         const long long src = row * ld_vec + (static_cast<long long>(which) * heads + dest * hl_n + hl) * hd_vec + c;
@@ -628,8 +684,8 @@ extern "C" __attribute__((visibility("default"))) int wvd_ulysses_pack_qkv(const
     return WVD_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int wvd_ulysses_scatter_qkv(const void* qkv, int64_t ld, void* const* recv_ptrs, int64_t n_local, int heads,
-                                       int head_dim, int world, int rank, wvd_stream_t stream) {
+static int scatter_impl(const void* qkv, int64_t ld, void* const* recv_ptrs, int64_t n_local, int heads, int head_dim, int world,
+                        int rank, int which0, wvd_stream_t stream) {
     WVD_REQUIRE(world >= 1 && world <= WVD_MAX_PEERS && rank >= 0 && rank < world, "wvd_ulysses_scatter_qkv: bad world/rank %d/%d", world, rank);
     WVD_REQUIRE(heads > 0 && heads % world == 0, "wvd_ulysses_scatter_qkv: heads (%d) must divide by world (%d)", heads, world);
     WVD_REQUIRE(head_dim % 8 == 0 && ld % 8 == 0 && ld >= 3ll * heads * head_dim, "wvd_ulysses_scatter_qkv: bad head_dim/ld");
@@ -640,9 +696,59 @@ extern "C" __attribute__((visibility("default"))) int wvd_ulysses_scatter_qkv(co
         pp.p[r] = r < world ? (uint4*)recv_ptrs[r] : nullptr;
         WVD_REQUIRE(r >= world || (pp.p[r] && aligned16(pp.p[r])), "wvd_ulysses_scatter_qkv: bad receive pointer of rank %d", r);
     }
-    const long long total = (long long)n_local * 3 * heads * (head_dim / 8);
+    const long long total = (long long)n_local * (3 - which0) * heads * (head_dim / 8);
     ew::ulysses_scatter_kernel<<<ew::stream_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const uint4*)qkv, ld / 8, pp, n_local, heads, head_dim / 8, world, rank);
+        (const uint4*)qkv, ld / 8, pp, n_local, heads, head_dim / 8, world, rank, which0);
+    WVD_CHECK_CUDA(cudaGetLastError());
+    return WVD_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_ulysses_scatter_qkv(const void* qkv, int64_t ld, void* const* recv_ptrs, int64_t n_local, int heads,
+                                       int head_dim, int world, int rank, wvd_stream_t stream) {
+    return scatter_impl(qkv, ld, recv_ptrs, n_local, heads, head_dim, world, rank, 0, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_ulysses_scatter_v(const void* qkv, int64_t ld, void* const* recv_ptrs, int64_t n_local, int heads,
+                                     int head_dim, int world, int rank, wvd_stream_t stream) {
+    return scatter_impl(qkv, ld, recv_ptrs, n_local, heads, head_dim, world, rank, 2, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_qk_rmsnorm_rope_scatter(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* wq,
+                                           const void* wk, void* const* recv_ptrs, int64_t n_local, int dim, int head_dim,
+                                           float eps, const void* rope_cs, const int32_t* frame_ids, int grid_f, int grid_h,
+                                           int grid_w, int64_t token_offset, int world, int rank, wvd_stream_t stream) {
+    WVD_REQUIRE(q && k && wq && wk && recv_ptrs && rope_cs, "wvd_qk_rmsnorm_rope_scatter: null pointer");
+    WVD_REQUIRE(head_dim == 128 && dim > 0 && dim % 128 == 0, "wvd_qk_rmsnorm_rope_scatter: head_dim must be 128 and divide dim");
+    WVD_REQUIRE(world >= 1 && world <= WVD_MAX_PEERS && rank >= 0 && rank < world, "wvd_qk_rmsnorm_rope_scatter: bad world/rank %d/%d", world, rank);
+    const int heads = dim / 128;
+    WVD_REQUIRE(heads % world == 0, "wvd_qk_rmsnorm_rope_scatter: heads (%d) must divide by world (%d)", heads, world);
+    WVD_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldq >= dim && ldk >= dim, "wvd_qk_rmsnorm_rope_scatter: bad ld");
+    WVD_REQUIRE(aligned16(q) && aligned16(k) && aligned16(wq) && aligned16(wk), "wvd_qk_rmsnorm_rope_scatter: pointers must be 16-byte aligned");
+    if (n_local == 0) return WVD_OK;
+    WVD_REQUIRE(n_local > 0, "wvd_qk_rmsnorm_rope_scatter: negative n_local");
+    WVD_REQUIRE(grid_f > 0 && grid_h > 0 && grid_w > 0 && grid_h <= 1024 && grid_w <= 1024 && (frame_ids != nullptr || grid_f <= 1024),
+                "wvd_qk_rmsnorm_rope_scatter: bad token grid %dx%dx%d", grid_f, grid_h, grid_w);
+    WVD_REQUIRE(token_offset >= 0 && token_offset <= (int64_t)grid_f * grid_h * grid_w, "wvd_qk_rmsnorm_rope_scatter: token_offset outside the grid");
+    ew::PeerPtrs pp;
+    for (int r = 0; r < WVD_MAX_PEERS; ++r) {
+        pp.p[r] = r < world ? (uint4*)recv_ptrs[r] : nullptr;
+        WVD_REQUIRE(r >= world || (pp.p[r] && aligned16(pp.p[r])), "wvd_qk_rmsnorm_rope_scatter: bad receive pointer of rank %d", r);
+    }
+    const int need = (dim / 8 + 31) / 32;
+    const dim3 grid(static_cast<unsigned>((n_local + ew::WARPS_PER_BLOCK - 1) / ew::WARPS_PER_BLOCK), 2);
+    const dim3 block(ew::WARPS_PER_BLOCK * 32);
+    cudaStream_t s = (cudaStream_t)stream;
+#define WVD_LAUNCH(MV)                                                                                                  \
+    ew::qk_rmsnorm_rope_scatter_kernel<MV><<<grid, block, 0, s>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, \
+        (const __nv_bfloat16*)wq, (const __nv_bfloat16*)wk, pp, n_local, dim, eps, (const float2*)rope_cs, frame_ids, grid_f,  \
+        grid_h, grid_w, token_offset, heads / world, rank)
+    if (need <= 2) WVD_LAUNCH(2);
+    else if (need <= 6) WVD_LAUNCH(6);
+    else if (need <= 12) WVD_LAUNCH(12);
+    else if (need <= 20) WVD_LAUNCH(20);
+    else if (need <= 40) WVD_LAUNCH(40);
+    else return set_error(WVD_ERR_UNSUPPORTED, "wvd_qk_rmsnorm_rope_scatter: dim %d too large", dim);
+#undef WVD_LAUNCH
     WVD_CHECK_CUDA(cudaGetLastError());
     return WVD_OK;
 }

@@ -172,6 +172,15 @@ class SelfAttnExchange:
         d = heads * 128
         return ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], heads, out=out)
 
+    def norm_rope_attend(self, ops, qkv: Tensor, heads: int, wq: Tensor, wk: Tensor, eps: float, rope: "RopeInfo",
+                         out: Tensor, ws: Workspace) -> Tensor:
+        """Full-width QK-RMSNorm + RoPE (before any head scatter, wan_video_dit.py:141-145 /
+        xdit_context_parallel.py:110-117), then attention.  The fused Ulysses exchange overrides this to let the
+        RoPE kernel store q and k straight into the peers' receive buffers."""
+        d = heads * 128
+        ops.qk_rmsnorm_rope(qkv[:, :d], qkv[:, d:2 * d], wq, wk, eps, rope.table, rope.grid, rope.token_offset, rope.frame_ids)
+        return self.attend(ops, qkv, heads, out, ws)
+
 
 _LOCAL = SelfAttnExchange()
 
@@ -195,9 +204,8 @@ def dit_block_forward(block, x: Tensor, context: Tensor, t_mod: Tensor, rope: Ro
     qkv = ws.get("qkv", (n, 3 * d))
     wb = [_lin(proj, dt, dev) for proj in (sa.q, sa.k, sa.v)]
     ops.linear_grouped(h, [w for w, _ in wb], [b for _, b in wb], out=qkv)        # one launch for q | k | v
-    ops.qk_rmsnorm_rope(qkv[:, :d], qkv[:, d:2 * d], _norm_w(sa.norm_q, dt, dev), _norm_w(sa.norm_k, dt, dev),
-                        _unwrap(sa.norm_q).eps, rope.table, rope.grid, rope.token_offset, rope.frame_ids)
-    a = exchange.attend(ops, qkv, heads, ws.get("attn", (n, d)), ws)
+    a = exchange.norm_rope_attend(ops, qkv, heads, _norm_w(sa.norm_q, dt, dev), _norm_w(sa.norm_k, dt, dev),
+                                  _unwrap(sa.norm_q).eps, rope, ws.get("attn", (n, d)), ws)
     w, b = _lin(sa.o, dt, dev)
     ops.linear(a, w, b, ops.EPI_BIAS_GATE_RES, gate=mod[2], residual=x, out=x)
     # ---- cross attention (ungated): x += o(attn(rms(q(norm3(x))), rms(k(ctx)), v(ctx))) ----

@@ -332,6 +332,35 @@ def ulysses_scatter_qkv(qkv: Tensor, heads: int, recv_ptrs, rank: int) -> None:
                                               world, rank, _stream()), "wvd_ulysses_scatter_qkv")
 
 
+def ulysses_scatter_v(qkv: Tensor, heads: int, recv_ptrs, rank: int) -> None:
+    """The v third of ``ulysses_scatter_qkv`` (q and k were stored into the peers by ``qk_rmsnorm_rope_scatter``)."""
+    qkv = _chk2d(qkv, "qkv")
+    world = len(recv_ptrs)
+    if qkv.dtype != torch.bfloat16 or qkv.shape[1] != 3 * heads * 128 or world > _lib.MAX_PEERS:
+        raise WvdError("ulysses_scatter_v: bf16 (n, 3*heads*128) and at most 8 ranks expected")
+    check(_lib.load().wvd_ulysses_scatter_v(qkv.data_ptr(), _ld(qkv), _ptr_array(recv_ptrs), qkv.shape[0], heads, 128,
+                                            world, rank, _stream()), "wvd_ulysses_scatter_v")
+
+
+def qk_rmsnorm_rope_scatter(q: Tensor, k: Tensor, wq: Tensor, wk: Tensor, eps: float, rope_table: Tensor,
+                            grid: Tuple[int, int, int], token_offset: int, frame_ids: Optional[Tensor], recv_ptrs,
+                            rank: int) -> None:
+    """``qk_rmsnorm_rope`` whose stores are the q / k part of the Ulysses exchange: every finished head goes straight
+    into the owning rank's receive buffer (peer pointers of a symmetric-memory rendezvous); q and k are NOT modified."""
+    q, k = _chk2d(q, "q"), _chk2d(k, "k")
+    n, d = q.shape
+    world = len(recv_ptrs)
+    if q.dtype != torch.bfloat16 or k.shape != q.shape or k.dtype != q.dtype or world > _lib.MAX_PEERS:
+        raise WvdError("qk_rmsnorm_rope_scatter: bf16 q / k of equal shape and at most 8 ranks expected")
+    if rope_table.dtype != torch.float32 or tuple(rope_table.shape) != (3, 1024, 32, 2) or not rope_table.is_cuda:
+        raise WvdError("rope_table must be the (3,1024,32,2) fp32 CUDA table from make_rope_table()")
+    wq, wk = _vec(wq, d, "norm_q.weight", q), _vec(wk, d, "norm_k.weight", q)
+    gf, gh, gw = grid
+    check(_lib.load().wvd_qk_rmsnorm_rope_scatter(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), wq.data_ptr(), wk.data_ptr(),
+                                                  _ptr_array(recv_ptrs), n, d, 128, eps, rope_table.data_ptr(), _p(frame_ids),
+                                                  gf, gh, gw, token_offset, world, rank, _stream()), "wvd_qk_rmsnorm_rope_scatter")
+
+
 def attention_scatter(q: Tensor, k: Tensor, v: Tensor, num_heads: int, out_ptrs, ldo: int, rows_per_peer: int,
                       col_offset: int, scale: Optional[float] = None, kernel: int = _lib.ATTN_AUTO) -> None:
     """ops.attention over the local heads whose epilogue stores query row t into rank t // rows_per_peer's

@@ -142,20 +142,43 @@ class P2PUlyssesExchange(UlyssesExchange):
             return None
         return self._buffers(n_loc, heads, device)        # a failure in here aborts the job (see _probe)
 
+    def norm_rope_attend(self, ops, qkv, heads: int, wq, wk, eps: float, rope, out, ws):
+        """The q / k part of the first all-to-all fused into the RoPE kernel's stores, the v part as a one-third
+        scatter: no pass over q and k between the RoPE kernel and the attention."""
+        p = self.world
+        if heads % p != 0:
+            raise ValueError(f"Ulysses needs num_heads ({heads}) divisible by the sequence-parallel world size ({p})")
+        per_token = tuple(rope.grid) == (0, 0, 0)
+        bufs = None if (per_token or qkv.dtype != torch.bfloat16) else self._buffers_or_none(qkv.shape[0], heads, qkv.device)
+        if bufs is None:
+            return super().norm_rope_attend(ops, qkv, heads, wq, wk, eps, rope, out, ws)
+        d = heads * 128
+        recv_ptrs = bufs[4]
+        # Safe to overwrite the peers' receive buffers: every rank passed the previous attention's second barrier only
+        # after its attention had finished reading them.
+        ops.qk_rmsnorm_rope_scatter(qkv[:, :d], qkv[:, d:2 * d], wq, wk, eps, rope.table, rope.grid, rope.token_offset,
+                                    rope.frame_ids, recv_ptrs, self.rank)
+        ops.ulysses_scatter_v(qkv, heads, recv_ptrs, self.rank)
+        return self._attend_received(ops, bufs, heads, qkv.shape[0])
+
     def attend(self, ops, qkv, heads: int, out, ws):
         p, r = self.world, self.rank
         if heads % p != 0:
             raise ValueError(f"Ulysses needs num_heads ({heads}) divisible by the sequence-parallel world size ({p})")
         n_loc = qkv.shape[0]
-        hl = heads // p
-        w = hl * 128
         bufs = self._buffers_or_none(n_loc, heads, qkv.device)
         if bufs is None:
             return super().attend(ops, qkv, heads, out, ws)
-        recv, aout, h_recv, h_out, recv_ptrs, out_ptrs = bufs
         # (1) q|k|v -> every rank's receive buffer.  Safe to overwrite: every rank passed the previous barrier (2)
         #     only after its previous attention had finished reading.
-        ops.ulysses_scatter_qkv(qkv, heads, recv_ptrs, r)
+        ops.ulysses_scatter_qkv(qkv, heads, bufs[4], r)
+        return self._attend_received(ops, bufs, heads, n_loc)
+
+    def _attend_received(self, ops, bufs, heads: int, n_loc: int):
+        p, r = self.world, self.rank
+        hl = heads // p
+        w = hl * 128
+        recv, aout, h_recv, h_out, recv_ptrs, out_ptrs = bufs
         h_recv.barrier(channel=0)
         n = self.n_tokens                       # rows >= n are the zero padding of the last shard: never attended
         # (2) attention over my heads and all tokens; rows go straight to their owners' o-projection input.  Safe to
