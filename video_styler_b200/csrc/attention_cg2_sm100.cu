@@ -16,6 +16,16 @@
 // reads a third fewer operand bytes from shared memory per MMA (Q 4 KB + K 2 KB instead of 4 + 4; V 2 instead of 4), and
 // one thread issues for both tiles (half the issue / barrier work per tile).  The step is power-capped (DESIGN.md
 // section 4): bytes moved are clock speed.
+// What sets the period (in-kernel timeline, profiles/r2_attention_cg2_timeline.txt): QK^T(j+2) overwrites the buffer of
+// P(j-1), so it is issued after the LAST hand-over of softmax(j-1); from there ~2,090 cycles of issue, mbarrier wake-up and
+// MMA latency pass until the softmax warps see S(j+2), then ~2,300 cycles of softmax(j+2): 4,390 cycles per THREE KV steps.
+// Tried on this kernel and dropped (tools/attn_ab.py, sustained A/B, profiles/r2_attention_ab.txt):
+//   exp2 of 1 or 2 of every 4 column pairs on the FMA pipes ........................ +4 % / +12 % time
+//   row maximum in the shadow of speculative exponentials against the stale reference  +5 %
+//   P in its own TMEM buffers (S_0 S_1 | P_0 P_1 | O) and separate QK^T / PV issuing threads, QK^T(j+2) issued as soon as
+//   softmax(j) has LOADED S(j): the softmax warps never wait for S any more, but ... +2 % (an extra mbarrier wait per tile on
+//   their path, both warpgroups contending all the time)
+//   the next step's K/V wait hoisted above the P waits + local instead of cluster-mapped arrive on the leader ... +3 %
 // Only the LEADER CTA (cluster rank 0) issues MMAs.  Both CTAs' TMA loads complete on the leader's barriers
 // (cp.async.bulk.tensor .cta_group::2), both CTAs' softmax warps hand P over on the leader's barriers (remote arrive),
 // tcgen05.commit is multicast to the S-full / slot-free / PV-done barriers of both CTAs.
@@ -55,10 +65,6 @@ constexpr int SMEM_BYTES = Q_BYTES + SLOTS * SLOT_BYTES + BAR_BYTES + XCHG_BYTES
 constexpr uint32_t IDESC_QK = make_idesc_bf16(256, 128, 0, 0);   // A = Q (K-major), B = K (K-major), M = 256 over the pair
 constexpr uint32_t IDESC_PV = make_idesc_bf16(256, 128, 0, 1);   // A = P (TMEM), B = V (MN-major)
 constexpr float REF_MARGIN = 8.0f;
-#ifndef WVD_ATTN3_EMU
-#define WVD_ATTN3_EMU 0
-#endif
-constexpr int EMU = WVD_ATTN3_EMU;            // of every 4 column pairs, how many take exp2 on the FMA pipes (polynomial) instead of MUFU
 
 struct Params {
     __nv_bfloat16* out;
@@ -308,14 +314,14 @@ attention_cg2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             for (int q8 = 0; q8 < BKV / GC; ++q8) {
                 uint32_t pk[GC / 2];
                 switch (q8) {   // compile-time after unrolling
-                    case 0: lsum += exp_chunk<BKV, 0 * GC, 1 * GC, EMU>(s, pk, sl2_2, negm_2); break;
-                    case 1: lsum += exp_chunk<BKV, 1 * GC, 2 * GC, EMU>(s, pk, sl2_2, negm_2); break;
-                    case 2: lsum += exp_chunk<BKV, 2 * GC, 3 * GC, EMU>(s, pk, sl2_2, negm_2); break;
-                    case 3: lsum += exp_chunk<BKV, 3 * GC, 4 * GC, EMU>(s, pk, sl2_2, negm_2); break;
-                    case 4: lsum += exp_chunk<BKV, 4 * GC, 5 * GC, EMU>(s, pk, sl2_2, negm_2); break;
-                    case 5: lsum += exp_chunk<BKV, 5 * GC, 6 * GC, EMU>(s, pk, sl2_2, negm_2); break;
-                    case 6: lsum += exp_chunk<BKV, 6 * GC, 7 * GC, EMU>(s, pk, sl2_2, negm_2); break;
-                    default: lsum += exp_chunk<BKV, 7 * GC, 8 * GC, EMU>(s, pk, sl2_2, negm_2); break;
+                    case 0: lsum += exp_chunk<BKV, 0 * GC, 1 * GC, 0>(s, pk, sl2_2, negm_2); break;
+                    case 1: lsum += exp_chunk<BKV, 1 * GC, 2 * GC, 0>(s, pk, sl2_2, negm_2); break;
+                    case 2: lsum += exp_chunk<BKV, 2 * GC, 3 * GC, 0>(s, pk, sl2_2, negm_2); break;
+                    case 3: lsum += exp_chunk<BKV, 3 * GC, 4 * GC, 0>(s, pk, sl2_2, negm_2); break;
+                    case 4: lsum += exp_chunk<BKV, 4 * GC, 5 * GC, 0>(s, pk, sl2_2, negm_2); break;
+                    case 5: lsum += exp_chunk<BKV, 5 * GC, 6 * GC, 0>(s, pk, sl2_2, negm_2); break;
+                    case 6: lsum += exp_chunk<BKV, 6 * GC, 7 * GC, 0>(s, pk, sl2_2, negm_2); break;
+                    default: lsum += exp_chunk<BKV, 7 * GC, 8 * GC, 0>(s, pk, sl2_2, negm_2); break;
                 }
                 store_p<GC / 2>(s_tmem + q8 * (GC / 2), pk);
                 if (q8 == HO0_GROUPS - 1 || q8 == BKV / GC - 1) {
