@@ -179,14 +179,20 @@ class P2PUlyssesExchange(UlyssesExchange):
         hl = heads // p
         w = hl * 128
         recv, aout, h_recv, h_out, recv_ptrs, out_ptrs = bufs
-        h_recv.barrier(channel=0)
+        _device_barrier(h_recv, "after scatter")
         n = self.n_tokens                       # rows >= n are the zero padding of the last shard: never attended
         # (2) attention over my heads and all tokens; rows go straight to their owners' o-projection input.  Safe to
         #     overwrite: every rank entered barrier (1) only after its previous o-projection had been enqueued
         #     ahead of it on its stream.
         ops.attention_scatter(recv[:n, :w], recv[:n, w:2 * w], recv[:n, 2 * w:], hl, out_ptrs, heads * 128, n_loc, r * w)
-        h_out.barrier(channel=0)
+        _device_barrier(h_out, "after attention")
         return aout
+
+
+def _device_barrier(handle, what: str) -> None:
+    """Cross-rank barrier on the current stream (symmetric-memory signal pads: a kernel, no host synchronisation).
+    One call site per barrier kind so that tools/step_breakdown.py can bracket them."""
+    handle.barrier(channel=0)
 
 
 def _host_id() -> str:
