@@ -123,13 +123,16 @@ int wvd_gemm_bf16_grouped(const void* A, int64_t lda, const void* const* W, int6
 int wvd_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                       void* out, int64_t ldo, int num_heads, int64_t sq, int64_t sk, int head_dim, float scale,
                       wvd_stream_t stream);
-/* Three kernels sit behind it: WVD_ATTN_TWO_TILE (two Q tiles per CTA; the 512-key text cross-attention),
- * WVD_ATTN_CG2 (2-CTA clusters, one tcgen05.mma cta_group::2 stream with M = 256 over the pair, K/V split over the pair,
- * triple-buffered S in TMEM; long self-attention) and WVD_ATTN_PAIR (its cta_group::1 predecessor: K/V multicast to both
- * CTAs; kept for A/B).  WVD_ATTN_AUTO picks by key length (CG2 for sk >= 2048) and is what wvd_attention_fwd uses.  The
- * selector is an ARGUMENT -- the library keeps no mutable dispatch state -- so that the parity tests can run all kernels
- * on the same inputs.                                                                                              */
-enum { WVD_ATTN_AUTO = 0, WVD_ATTN_TWO_TILE = 1, WVD_ATTN_PAIR = 2, WVD_ATTN_CG2 = 3 };
+/* Four kernels sit behind it: WVD_ATTN_ONE_TILE (one 128-row Q tile per CTA, 256 TMEM columns, two CTAs per SM: the
+ * 512-key text cross-attention, where prologue and epilogue are as long as the 4-step main loop), WVD_ATTN_TWO_TILE (two Q
+ * tiles per CTA, one CTA per SM: medium key lengths), WVD_ATTN_CG2 (2-CTA clusters, one tcgen05.mma cta_group::2 stream
+ * with M = 256 over the pair, K/V split over the pair, triple-buffered S in TMEM; long self-attention) and WVD_ATTN_PAIR
+ * (its cta_group::1 predecessor: K/V multicast to both CTAs; kept for A/B).  WVD_ATTN_AUTO picks by key length (ONE_TILE
+ * for sk <= 1024, CG2 for sk >= 2048) and is what wvd_attention_fwd uses.  The selector is an ARGUMENT -- the library
+ * keeps no mutable dispatch state -- so that the parity tests can run all kernels on the same inputs.               */
+enum { WVD_ATTN_AUTO = 0, WVD_ATTN_TWO_TILE = 1, WVD_ATTN_PAIR = 2, WVD_ATTN_CG2 = 3, WVD_ATTN_ONE_TILE = 4 };
+/* Resident CTAs per SM of the short-key kernel `which` (WVD_ATTN_ONE_TILE: 2 by construction); < 0 = error. */
+int wvd_debug_attention_resident_ctas(int which);
 int wvd_attention_fwd_select(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                              void* out, int64_t ldo, int num_heads, int64_t sq, int64_t sk, int head_dim, float scale,
                              int which, wvd_stream_t stream);

@@ -16,6 +16,7 @@ SIGNATURES = {
     "wvd_version": [],
     "wvd_sm_arch": [],
     "wvd_debug_flags": [ctypes.POINTER(ctypes.c_ulonglong)],
+    "wvd_debug_attention_resident_ctas": [ctypes.c_int],
     "wvd_ln_modulate": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                         c_float, c_int, c_void_p],
     "wvd_qk_rmsnorm_rope": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
@@ -51,7 +52,7 @@ MAX_PEERS = 8
 
 WVD_BF16, WVD_F32 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_GATE_RES = 0, 1, 2, 3
-ATTN_AUTO, ATTN_TWO_TILE, ATTN_PAIR, ATTN_CG2 = 0, 1, 2, 3
+ATTN_AUTO, ATTN_TWO_TILE, ATTN_PAIR, ATTN_CG2, ATTN_ONE_TILE = 0, 1, 2, 3, 4
 GEMM_AUTO, GEMM_1CTA, GEMM_2CTA, GEMM_2CTA_M512 = 0, 1, 2, 3
 
 _lib = None

@@ -346,31 +346,20 @@ attention_cg2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const float inv_l = 1.0f / (l + __uint_as_float(ld_shared_volatile_u32(l_other_addr)));
         mbar_wait(o_full, 0, 0x310);
         tc_fence_after();
-        __nv_bfloat16* orow;
-        if (p.rows_per_peer > 0) {
-            const int dest = row / p.rows_per_peer;
-            orow = p.out_peer[dest < WVD_MAX_PEERS ? dest : 0] + static_cast<long long>(row - dest * p.rows_per_peer) * p.ldo;
-        } else {
-            orow = p.out + static_cast<long long>(row) * p.ldo;
-        }
-        orow += head * HD + g * (HD / 2);
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(o_tmem + g * (HD / 2) + c * 32, o);
-            tc_wait_ld();
-            if (row < p.sq) {
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    uint4 u;
-                    u.x = pack_bf16x2(__uint_as_float(o[q4 * 8 + 0]) * inv_l, __uint_as_float(o[q4 * 8 + 1]) * inv_l);
-                    u.y = pack_bf16x2(__uint_as_float(o[q4 * 8 + 2]) * inv_l, __uint_as_float(o[q4 * 8 + 3]) * inv_l);
-                    u.z = pack_bf16x2(__uint_as_float(o[q4 * 8 + 4]) * inv_l, __uint_as_float(o[q4 * 8 + 5]) * inv_l);
-                    u.w = pack_bf16x2(__uint_as_float(o[q4 * 8 + 6]) * inv_l, __uint_as_float(o[q4 * 8 + 7]) * inv_l);
-                    *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = u;
-                }
+        // All MMAs of the pair have completed (o_full): my CTA's Q tile is dead, its 32 KB stage the output (4 KB per warp).
+        const int wrow0 = q_row0 + quarter * 32;
+        attn::store_o_warp_coalesced(o_tmem + g * (HD / 2), inv_l, q_smem + warp * 4096, lane, [&](int rr) -> __nv_bfloat16* {
+            const int grow = wrow0 + rr;
+            if (grow >= p.sq) return nullptr;
+            __nv_bfloat16* base;
+            if (p.rows_per_peer > 0) {
+                const int dest = grow / p.rows_per_peer;
+                base = p.out_peer[dest < WVD_MAX_PEERS ? dest : 0] + static_cast<long long>(grow - dest * p.rows_per_peer) * p.ldo;
+            } else {
+                base = p.out + static_cast<long long>(grow) * p.ldo;
             }
-        }
+            return base + head * HD + g * (HD / 2);
+        });
     }
 
     tc_fence_before();

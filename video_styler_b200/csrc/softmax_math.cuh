@@ -73,5 +73,60 @@ __device__ __forceinline__ void store_p(uint32_t taddr, const uint32_t* pk) {
     if (NCOL % 16 != 0) tmem_st_32x32b_x8(taddr + (NCOL / 16) * 16, pk + (NCOL / 16) * 16);
 }
 
+
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+// Epilogue of the attention kernels: a warp holds 32 query rows (one per lane) x 64 output columns as fp32 in TMEM
+// (o_tmem = lane quarter + first column); out = O * inv_l as bf16, 128 bytes per row.
+// A direct store from the TMEM-load layout makes every warp store touch 32 different rows (32 wavefronts of 16 bytes per
+// instruction).
+// Instead the warp stages its 4 KB through shared memory (XOR-swizzled 16-byte chunks: conflict-free both ways) and
+// writes 4 full 128-byte row segments per instruction (4 wavefronts): 8x fewer LSU cycles.
+// row_ptr(rr) returns the global address of columns [0, 64) of the warp's row rr (0..31), or nullptr for rows past the end
+// (evaluated by the lanes that STORE row rr, so the Ulysses per-peer address computation works row by row).
+// stage: TMEM -> (x inv_l, bf16) -> the warp's 4 KB of shared memory; after it returns the warp's O columns are out of TMEM
+__device__ __forceinline__ void stage_o_warp(uint32_t o_tmem, float inv_l, uint32_t stage, int lane) {
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(o_tmem + c * 32, o);
+        tc_wait_ld();
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            const int chunk = c * 4 + q4;
+            st_shared_v4(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4),
+                         pack_bf16x2(__uint_as_float(o[q4 * 8 + 0]) * inv_l, __uint_as_float(o[q4 * 8 + 1]) * inv_l),
+                         pack_bf16x2(__uint_as_float(o[q4 * 8 + 2]) * inv_l, __uint_as_float(o[q4 * 8 + 3]) * inv_l),
+                         pack_bf16x2(__uint_as_float(o[q4 * 8 + 4]) * inv_l, __uint_as_float(o[q4 * 8 + 5]) * inv_l),
+                         pack_bf16x2(__uint_as_float(o[q4 * 8 + 6]) * inv_l, __uint_as_float(o[q4 * 8 + 7]) * inv_l));
+        }
+    }
+    __syncwarp();
+}
+
+// flush: the staged 32 rows x 128 bytes -> global, 4 whole row segments per warp instruction
+template <typename RowPtr>
+__device__ __forceinline__ void flush_o_warp(uint32_t stage, int lane, RowPtr row_ptr) {
+    const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + sub;
+        const uint4 v = ld_shared_v4(stage + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+        __nv_bfloat16* dst = row_ptr(rr);
+        if (dst != nullptr) *reinterpret_cast<uint4*>(dst + chunk * 8) = v;
+    }
+    __syncwarp();
+}
+
+template <typename RowPtr>
+__device__ __forceinline__ void store_o_warp_coalesced(uint32_t o_tmem, float inv_l, uint32_t stage, int lane, RowPtr row_ptr) {
+    stage_o_warp(o_tmem, inv_l, stage, lane);
+    flush_o_warp(stage, lane, row_ptr);
+}
+
 }  // namespace attn
 }  // namespace wvd
