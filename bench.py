@@ -442,7 +442,7 @@ def main():
                              d2h_bytes_per_step=out_host.numel() * 2),
                     gpu_launches=launches,
                     clocks=clocks,
-                    roofline=dict(bound="tensor", kernel="wvd::attn2::attention_pair_kernel (self-attention)",
+                    roofline=dict(bound="tensor", kernel="wvd::attn4::attention_cg2p_kernel (self-attention, persistent cta_group::2)",
                                   achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s",
                                   frac=(achieved / pk["bf16_sustained"]) if achieved else None,
                                   traffic=ncu_traffic_bytes() if args.workload == "c3" and world == 1 else None,

@@ -130,7 +130,7 @@ int wvd_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, co
  * (its cta_group::1 predecessor: K/V multicast to both CTAs; kept for A/B).  WVD_ATTN_AUTO picks by key length (ONE_TILE
  * for sk <= 1024, CG2 for sk >= 2048) and is what wvd_attention_fwd uses.  The selector is an ARGUMENT -- the library
  * keeps no mutable dispatch state -- so that the parity tests can run all kernels on the same inputs.               */
-enum { WVD_ATTN_AUTO = 0, WVD_ATTN_TWO_TILE = 1, WVD_ATTN_PAIR = 2, WVD_ATTN_CG2 = 3, WVD_ATTN_ONE_TILE = 4 };
+enum { WVD_ATTN_AUTO = 0, WVD_ATTN_TWO_TILE = 1, WVD_ATTN_PAIR = 2, WVD_ATTN_CG2 = 3, WVD_ATTN_ONE_TILE = 4, WVD_ATTN_CG2_PERSISTENT = 5 };
 /* Resident CTAs per SM of the short-key kernel `which` (WVD_ATTN_ONE_TILE: 2 by construction); < 0 = error. */
 int wvd_debug_attention_resident_ctas(int which);
 int wvd_attention_fwd_select(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

@@ -220,7 +220,8 @@ def _attn_ref(q, k, v, h, dtype=torch.float32):
     return O.attention(q[None].to(dtype), k[None].to(dtype), v[None].to(dtype), h)[0]
 
 
-@pytest.fixture(params=[1, 2, 3, 4], ids=["two_tile_kernel", "cta_pair_kernel", "cta_group2_kernel", "one_tile_kernel"])
+@pytest.fixture(params=[1, 2, 3, 4, 5], ids=["two_tile_kernel", "cta_pair_kernel", "cta_group2_kernel", "one_tile_kernel",
+                                          "cta_group2_persistent_kernel"])
 def attn_kernel(request):
     """Run the test on ALL bf16 attention kernels (the default dispatch picks by key length)."""
     return request.param

@@ -33,7 +33,8 @@ k4 = qkv[:, d:2 * d].reshape(1, n, h, 128).transpose(1, 2)
 v4 = qkv[:, 2 * d:].reshape(1, n, h, 128).transpose(1, 2)
 cont = [("sdpa", lambda: F.scaled_dot_product_attention(q4, k4, v4)),
         ("wvd-pair(cg1)", lambda: ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h, out=out, kernel=_lib.ATTN_PAIR)),
-        ("wvd-cg2", lambda: ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h, out=out, kernel=_lib.ATTN_CG2))]
+        ("wvd-cg2", lambda: ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h, out=out, kernel=_lib.ATTN_CG2)),
+        ("wvd-cg2-persistent", lambda: ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h, out=out, kernel=_lib.ATTN_CG2_PERSISTENT))]
 fl = 4.0 * n * n * d
 ref = F.scaled_dot_product_attention(q4, k4, v4).transpose(1, 2).reshape(n, d)
 lines = []

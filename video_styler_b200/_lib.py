@@ -52,7 +52,7 @@ MAX_PEERS = 8
 
 WVD_BF16, WVD_F32 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_GATE_RES = 0, 1, 2, 3
-ATTN_AUTO, ATTN_TWO_TILE, ATTN_PAIR, ATTN_CG2, ATTN_ONE_TILE = 0, 1, 2, 3, 4
+ATTN_AUTO, ATTN_TWO_TILE, ATTN_PAIR, ATTN_CG2, ATTN_ONE_TILE, ATTN_CG2_PERSISTENT = 0, 1, 2, 3, 4, 5
 GEMM_AUTO, GEMM_1CTA, GEMM_2CTA, GEMM_2CTA_M512 = 0, 1, 2, 3
 
 _lib = None

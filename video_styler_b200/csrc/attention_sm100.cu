@@ -479,12 +479,15 @@ int attention_pair_launch(const void* q, int64_t ldq, const void* k, int64_t ldk
 int attention_cg2_launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                          void* const* out_peers, int world, int64_t rows_per_peer, int64_t ldo, int num_heads,
                          int64_t sq, int64_t sk, float scale, cudaStream_t st);
+int attention_cg2p_launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                          void* const* out_peers, int world, int64_t rows_per_peer, int64_t ldo, int num_heads,
+                          int64_t sq, int64_t sk, float scale, cudaStream_t st);
 namespace attn {
 static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                   void* const* out_peers, int world, int64_t rows_per_peer, int64_t ldo, int num_heads, int64_t sq,
                   int64_t sk, int head_dim, float scale, int which, wvd_stream_t stream) {
     WVD_REQUIRE(q && k && v && (out || out_peers), "wvd_attention_fwd: null pointer");
-    WVD_REQUIRE(which >= WVD_ATTN_AUTO && which <= WVD_ATTN_ONE_TILE, "wvd_attention_fwd: bad kernel selector %d", which);
+    WVD_REQUIRE(which >= WVD_ATTN_AUTO && which <= WVD_ATTN_CG2_PERSISTENT, "wvd_attention_fwd: bad kernel selector %d", which);
     WVD_REQUIRE(head_dim == HD, "wvd_attention_fwd: head_dim must be 128 (got %d)", head_dim);
     WVD_REQUIRE(num_heads > 0 && num_heads <= 65535, "wvd_attention_fwd: bad num_heads %d", num_heads);
     WVD_REQUIRE(sq > 0 && sk > 0 && sq < (1ll << 31) && sk < (1ll << 31), "wvd_attention_fwd: bad sequence lengths sq=%lld sk=%lld", (long long)sq, (long long)sk);
@@ -535,7 +538,10 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
     // (attention_pair_sm100.cu, K/V multicast to both CTAs) stays selectable for A/B.  Short ones (the 512-token text cross-attention: 4 KV steps,
     // prologue-dominated) stay on the two-tile kernel of this file.  `which` is an explicit ARGUMENT (the parity
     // tests run both kernels on the same inputs): the library keeps no mutable selection state.
-    if (which == WVD_ATTN_CG2 || (which == WVD_ATTN_AUTO && sk >= 2048))
+    if (which == WVD_ATTN_CG2_PERSISTENT || (which == WVD_ATTN_AUTO && sk >= 2048))
+        return attention_cg2p_launch(q, ldq, k, ldk, v, ldv, out, out_peers ? (void* const*)p.out_peer : nullptr, world,
+                                     rows_per_peer, ldo, num_heads, sq, sk, scale, st);
+    if (which == WVD_ATTN_CG2)
         return attention_cg2_launch(q, ldq, k, ldk, v, ldv, out, out_peers ? (void* const*)p.out_peer : nullptr, world,
                                     rows_per_peer, ldo, num_heads, sq, sk, scale, st);
     if (which == WVD_ATTN_PAIR)

@@ -85,7 +85,10 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 // try_wait (SYNCS...TRYWAIT: the warp sleeps in hardware until the phase flips or an implementation-defined limit
 // expires); the form with a suspend-time hint compiles to a NANOSLEEP polling loop that wakes ~16 times per wait and
 // steals issue slots from the warps that are working (ncu source page, profiles/).  Deadlock guard: wall clock every
-// 64 failed probes.
+// 64 failed probes.  The ~10 instructions of bookkeeping per failed probe are 70 % of the GEMM's executed instructions
+// (ncu source page), but they act as a back-off: a tight 3-instruction probe loop (1,024 probes per watchdog check) made
+// the GEMMs 2-3 % and the persistent attention kernel 2.5 % SLOWER (profiles/r2_attention_ab.txt) -- faster probing takes
+// shared-memory and issue bandwidth from the warps that work.
 #ifndef WVD_WAIT_TIMEOUT_NS
 #define WVD_WAIT_TIMEOUT_NS 4000000000ull
 #endif
