@@ -74,12 +74,6 @@ def main():
             step()
         plain_ms = timed(step, a.steps)
         graph_ms = None
-        if a.graph:
-            g = V.GraphedModelFn(dit=dit, vace=vace, vace_scale=1.0, use_unified_sequence_parallel=usp)
-            gf = lambda: g(inp["latents"], ts, inp["context"], inp.get("vace_context"))     # noqa: E731
-            gf()
-            graph_ms = timed(gf, a.steps)
-
         # ---- bracket every op ----
         records = {}
 
@@ -128,6 +122,16 @@ def main():
             setattr(mod, name, fn)
         U._device_barrier = orig_barrier
 
+    graph_err = None
+    if a.graph:          # last: a failed capture can leave the stream unusable
+        try:
+            with torch.no_grad():
+                g = V.GraphedModelFn(dit=dit, vace=vace, vace_scale=1.0, use_unified_sequence_parallel=usp)
+                gf = lambda: g(inp["latents"], ts, inp["context"], inp.get("vace_context"))     # noqa: E731
+                gf()
+                graph_ms = timed(gf, a.steps)
+        except Exception as e:      # noqa: BLE001
+            graph_err = repr(e)[:300]
     fams = sorted(records)
     tot = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in records[f]) / a.steps for f in fams], device=dev, dtype=torch.float64)
     cnt = [len(records[f]) / a.steps for f in fams]
@@ -144,9 +148,15 @@ def main():
             print(f"  {f:42s} {c:13.1f} {t:14.3f} {tm:15.3f} {100 * t / inst_ms:13.1f}%")
         print(f"  {'(sum of the bracketed ops, rank 0)':42s} {sum(cnt):13.1f} {covered:14.3f} {'':15s} {100 * covered / inst_ms:13.1f}%")
         print(f"  {'gaps: glue kernels, launch latency, idle':42s} {'':13s} {inst_ms - covered:14.3f} {'':15s} {100 * (inst_ms - covered) / inst_ms:13.1f}%")
+        if graph_err:
+            print("# CUDA-graph capture failed:", graph_err)
         if a.json:
             json.dump(dict(workload=a.workload, world=world, plain_ms=plain_ms, graph_ms=graph_ms, instrumented_ms=inst_ms,
                            families=[dict(name=f, launches=c, ms=t, ms_max=tm) for f, c, t, tm in rows]), open(a.json, "w"), indent=1)
+    sys.stdout.flush()
+    torch.cuda.synchronize()
+    if a.graph:
+        os._exit(0)      # destroying an NCCL communicator that live CUDA graphs still reference hangs: just leave
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

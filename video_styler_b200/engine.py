@@ -203,7 +203,14 @@ def dit_block_forward(block, x: Tensor, context: Tensor, t_mod: Tensor, rope: Ro
     h = ops.ln_modulate(x, mod[0], mod[1], eps=eps, out=ws.get("h", (n, d)))
     qkv = ws.get("qkv", (n, 3 * d))
     wb = [_lin(proj, dt, dev) for proj in (sa.q, sa.k, sa.v)]
-    ops.linear_grouped(h, [w for w, _ in wb], [b for _, b in wb], out=qkv)        # one launch for q | k | v
+    if exchange.world > 1 and hasattr(exchange, "v_ready"):
+        # Ulysses: v first, so that its scatter over NVLink (which needs nothing from the RMSNorm / RoPE of q and k) runs
+        # on a side stream under the q | k projection instead of after it
+        ops.linear(h, wb[2][0], wb[2][1], out=qkv[:, 2 * d:])
+        exchange.v_ready(ops, qkv, heads)
+        ops.linear_grouped(h, [wb[0][0], wb[1][0]], [wb[0][1], wb[1][1]], out=qkv[:, :2 * d])
+    else:
+        ops.linear_grouped(h, [w for w, _ in wb], [b for _, b in wb], out=qkv)    # one launch for q | k | v
     a = exchange.norm_rope_attend(ops, qkv, heads, _norm_w(sa.norm_q, dt, dev), _norm_w(sa.norm_k, dt, dev),
                                   _unwrap(sa.norm_q).eps, rope, ws.get("attn", (n, d)), ws)
     w, b = _lin(sa.o, dt, dev)
@@ -226,11 +233,12 @@ def dit_block_forward(block, x: Tensor, context: Tensor, t_mod: Tensor, rope: Ro
         kc, vc = cached[0], cached[1]
     else:
         own = text_entry is not None                     # cached K / V live in their own buffers, not in the workspace
-        w, b = _lin(ca.k, dt, dev)
-        kc = ops.linear(context, w, b, out=torch.empty((lc, d), dtype=dt, device=dev) if own else ws.get("kc", (lc, d)))
+        # k | v projections of the text in ONE launch (two M = 512 GEMMs of 80 tiles each leave half the SMs idle)
+        kv = torch.empty((lc, 2 * d), dtype=dt, device=dev) if own else ws.get("kvc", (lc, 2 * d))
+        (wk, bk), (wv, bv) = _lin(ca.k, dt, dev), _lin(ca.v, dt, dev)
+        ops.linear_grouped(context, [wk, wv], [bk, bv], out=kv)
+        kc, vc = kv[:, :d], kv[:, d:]
         ops.qk_rmsnorm_rope(kc, None, _norm_w(ca.norm_k, dt, dev), None, _unwrap(ca.norm_k).eps)
-        w, b = _lin(ca.v, dt, dev)
-        vc = ops.linear(context, w, b, out=torch.empty((lc, d), dtype=dt, device=dev) if own else ws.get("vc", (lc, d)))
         if own:
             text_entry["kv"][id(block)] = (kc, vc, stamp)
     a = ops.attention(q, kc, vc, heads, out=ws.get("attn", (n, d)))

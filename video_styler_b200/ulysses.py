@@ -100,6 +100,31 @@ class P2PUlyssesExchange(UlyssesExchange):
             self._bufs[key] = (recv, aout, h_recv, h_out, [int(x) for x in h_recv.buffer_ptrs], [int(x) for x in h_out.buffer_ptrs])
         return self._bufs[key]
 
+    _v_sent = False
+
+    def v_ready(self, ops, qkv, heads: int) -> None:
+        """The v columns of ``qkv`` are final on the current stream: store them into the peers on the side stream.
+        Safe to overwrite the peers' receive buffers: every rank passed the previous attention's second barrier only
+        after its attention had finished reading them.  No-op (the NCCL path packs everything later) when the
+        peer-memory buffers are unavailable."""
+        if heads % self.world != 0 or qkv.dtype != torch.bfloat16:
+            return
+        bufs = self._buffers_or_none(qkv.shape[0], heads, qkv.device)
+        if bufs is None:
+            return
+        main = torch.cuda.current_stream()
+        side = self._side_stream(qkv.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.ulysses_scatter_v(qkv, heads, bufs[4], self.rank)
+        self._v_sent = True
+
+    def _side_stream(self, device):
+        st = getattr(self, "_side", None)
+        if st is None:
+            st = self._side = torch.cuda.Stream(device=device)
+        return st
+
     def _probe(self, device) -> bool:
         """Can EVERY rank take the peer-memory path?  Local, failure-free checks (symmetric-memory module importable,
         peer access to every GPU of the group) agreed on with one all-reduce BEFORE anybody enters the rendezvous:
@@ -151,14 +176,24 @@ class P2PUlyssesExchange(UlyssesExchange):
         per_token = tuple(rope.grid) == (0, 0, 0)
         bufs = None if (per_token or qkv.dtype != torch.bfloat16) else self._buffers_or_none(qkv.shape[0], heads, qkv.device)
         if bufs is None:
+            if self._v_sent:            # announced, but this call takes the collective path after all: just rejoin
+                torch.cuda.current_stream().wait_stream(self._side_stream(qkv.device))
+                self._v_sent = False
             return super().norm_rope_attend(ops, qkv, heads, wq, wk, eps, rope, out, ws)
         d = heads * 128
         recv_ptrs = bufs[4]
         # Safe to overwrite the peers' receive buffers: every rank passed the previous attention's second barrier only
         # after its attention had finished reading them.
+        # The v third went out on the side stream right after its projection (v_ready), under the q | k projection; if
+        # the caller did not announce it, it goes now, still concurrently with the RoPE kernel's stores.
+        main = torch.cuda.current_stream()
+        side = self._side_stream(qkv.device)
+        if not self._v_sent:
+            self.v_ready(ops, qkv, heads)
+        self._v_sent = False
         ops.qk_rmsnorm_rope_scatter(qkv[:, :d], qkv[:, d:2 * d], wq, wk, eps, rope.table, rope.grid, rope.token_offset,
                                     rope.frame_ids, recv_ptrs, self.rank)
-        ops.ulysses_scatter_v(qkv, heads, recv_ptrs, self.rank)
+        main.wait_stream(side)
         return self._attend_received(ops, bufs, heads, qkv.shape[0])
 
     def attend(self, ops, qkv, heads: int, out, ws):
