@@ -32,7 +32,9 @@ enum {
     WVD_EPI_BIAS = 0,          /* C = y                                   nn.Linear (wan_video_dit.py:131-134) */
     WVD_EPI_BIAS_GELU = 1,     /* C = gelu_tanh(y)                        ffn.0 + nn.GELU('tanh') (:209-210)    */
     WVD_EPI_BIAS_RES = 2,      /* C = residual + y                        x + cross_attn(...) (:227); before_proj(c)+x (wan_video_vace.py:15) */
-    WVD_EPI_BIAS_GATE_RES = 3  /* C = residual + gate[n] * y              GateModule (:189-194, :226, :229)     */
+    WVD_EPI_BIAS_GATE_RES = 3, /* C = residual + gate[n] * y              GateModule (:189-194, :226, :229)     */
+    WVD_EPI_BIAS_MUL = 4,      /* C = y * residual (elementwise)          T5 gated FFN fc1(x) * gelu(gate(x)) (wan_video_text_encoder.py:108) */
+    WVD_EPI_BIAS_GELU_T5 = 5   /* C = 0.5 y (1 + tanh(c (y + 0.044715 y^3))) evaluated OP BY OP in the tensor dtype, the umT5 encoder's hand-written GELU (wan_video_text_encoder.py:16-20): seven roundings in bf16 */
 };
 
 /* ---- library info / diagnostics ------------------------------------------------------------------- */
@@ -87,6 +89,25 @@ int wvd_scale_add(const void* x, const void* y, float scale, void* out, int64_t 
  * reference's eager expressions.  v_nega == NULL (cfg_scale == 1): out = x + v_posi * dsigma.  out may alias x.     */
 int wvd_cfg_euler_step(const void* x, const void* v_posi, const void* v_nega, float cfg_scale, float dsigma, void* out,
                        int64_t n_elems, int dtype, wvd_stream_t stream);
+/* ---- Keyframe editor step (wan_video_editor.py:107-165 compute_velocity_correction, :362-390 CFG + split + Euler) ----
+ * One pass over the main latents (BC, T, HW) and the edited-keyframe latents (BC, K, HW): CFG combine (v_nega may be
+ * NULL), velocity correction at the keyframe positions (alpha, beta, dt as in the reference), then either the Euler
+ * update z + v * dsigma (euler = 1; flow_match.py:72-82) or the corrected velocities themselves (euler = 0), with the
+ * reference's per-operation rounding in `dtype`.  Velocities are (BC, frames, HW) slabs with explicit BC strides in
+ * elements (the joint (B, C, T+K, H, W) model output is read in place).  frame_to_key[t] = k or -1; key_idx[k] = t.   */
+int wvd_editor_step(const void* z_main, const void* z_edit, const void* vp_main, const void* vp_edit, const void* vn_main,
+                    const void* vn_edit, int64_t v_main_bc_stride, int64_t v_edit_bc_stride, const int* frame_to_key,
+                    const int* key_idx, int bc, int t_frames, int k_frames, int64_t hw, float cfg_scale, float dt, float alpha,
+                    float beta, float dsigma, int euler, void* out_main, void* out_edit, int dtype, wvd_stream_t stream);
+
+/* ---- K11: umT5 self-attention, head_dim 64, additive relative-position bias + key mask (wan_video_text_encoder.py:55-90) --
+ * out = softmax_j(q.k * scale + bias[h][(j - i) + lq - 1]; key_mask[j] == 0 -> finfo(dtype).min) v ; bias is a
+ * (heads, >= lq + lk - 1) table in `dtype` with row stride ld_bias (NULL = no bias), key_mask int32[lk] or NULL; fp32
+ * softmax; the reference's rounding points (scores, scores + bias, probabilities) are kept in bf16 mode.             */
+int wvd_attention_bias_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                           const void* bias, int64_t ld_bias, const int* key_mask, void* out, int64_t ldo, int num_heads,
+                           int64_t lq, int64_t lk, int head_dim, float scale, int dtype, wvd_stream_t stream);
+
 /* out = x + gate[c] * y (GateModule, wan_video_dit.py:189-194) -- only used when the producer is not a GEMM */
 int wvd_gate_residual(const void* x, const void* gate, const void* y, void* out, int64_t n_tokens, int dim,
                       int dtype, wvd_stream_t stream);

@@ -6,7 +6,7 @@ import torch.nn.functional as F
 
 from oracle import wan_oracle as O
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_GATE_RES = 0, 1, 2, 3
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_GATE_RES, EPI_BIAS_MUL, EPI_BIAS_GELU_T5 = 0, 1, 2, 3, 4, 5
 
 
 def as_2d(x):
@@ -76,6 +76,11 @@ def linear(x, weight, bias=None, epilogue=EPI_BIAS, gate=None, residual=None, ou
         y = residual + y
     elif epilogue == EPI_BIAS_GATE_RES:
         y = residual + gate * y
+    elif epilogue == EPI_BIAS_MUL:
+        y = y * residual
+    elif epilogue == EPI_BIAS_GELU_T5:
+        from oracle import aux_oracle as A
+        y = A.t5_gelu(y)
     return _ret(y, out)
 
 
@@ -84,6 +89,32 @@ def linear_grouped(x, weights, biases, out, variant=0):
     for i, (w, b) in enumerate(zip(weights, biases)):
         out[:, i * n:(i + 1) * n].copy_(F.linear(x, w, b))
     return out
+
+
+def attention_bias(q, k, v, num_heads, bias=None, key_mask=None, scale=1.0, out=None):
+    lq, lk = q.shape[0], k.shape[0]
+    qh, kh, vh = (t.view(t.shape[0], num_heads, 64).transpose(0, 1) for t in (q, k, v))
+    s = torch.matmul(qh, kh.transpose(1, 2)) * scale
+    b = torch.zeros_like(s)
+    if bias is not None:
+        idx = (torch.arange(lk)[None, :] - torch.arange(lq)[:, None]) + (lq - 1)
+        b = b + bias[:, idx]
+    if key_mask is not None:
+        b = b.masked_fill(key_mask.view(1, 1, lk) == 0, torch.finfo(q.dtype).min)
+    p = torch.softmax((s + b).float(), dim=-1).to(q.dtype)
+    return _ret(torch.matmul(p, vh).transpose(0, 1).reshape(lq, num_heads * 64), out)
+
+
+def editor_step(z_main, z_edit, v_posi, v_nega, frame_to_key, key_idx, cfg_scale, dt, alpha, beta, dsigma=0.0, euler=True):
+    from oracle import aux_oracle as A
+    join = lambda v: v if (v is None or torch.is_tensor(v)) else torch.cat(list(v), dim=2)      # noqa: E731
+    keys = [int(i) for i in key_idx]
+    vp, vn = join(v_posi), join(v_nega)
+    if euler:
+        return A.editor_step(z_main, z_edit, vp, vn, keys, cfg_scale, dt, alpha, beta, dsigma)
+    v = vp if vn is None else vn + cfg_scale * (vp - vn)
+    vm, ve = torch.split(v, [z_main.shape[2], z_edit.shape[2]], dim=2)
+    return A.velocity_correction(z_main, z_edit, vm, ve, keys, dt, alpha, beta)
 
 
 def attention(q, k, v, num_heads, out=None, scale=None):

@@ -24,6 +24,10 @@ SIGNATURES = {
                             c_int, c_void_p],
     "wvd_scale_add": [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p],
     "wvd_cfg_euler_step": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_int64, c_int, c_void_p],
+    "wvd_editor_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int,
+                        c_int, c_int, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "wvd_attention_bias_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                               c_int64, c_int, c_int64, c_int64, c_int, c_float, c_int, c_void_p],
     "wvd_gate_residual": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
     "wvd_gemm_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                       c_int, c_void_p, c_void_p, c_int64, c_void_p],
@@ -51,7 +55,7 @@ SIGNATURES = {
 MAX_PEERS = 8
 
 WVD_BF16, WVD_F32 = 0, 1
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_GATE_RES = 0, 1, 2, 3
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_GATE_RES, EPI_BIAS_MUL, EPI_BIAS_GELU_T5 = 0, 1, 2, 3, 4, 5
 ATTN_AUTO, ATTN_TWO_TILE, ATTN_PAIR, ATTN_CG2, ATTN_ONE_TILE, ATTN_CG2_PERSISTENT = 0, 1, 2, 3, 4, 5
 GEMM_AUTO, GEMM_1CTA, GEMM_2CTA, GEMM_2CTA_M512 = 0, 1, 2, 3
 

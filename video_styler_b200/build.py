@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libwvd.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "elementwise.cu", "gemm_sm100.cu", "attention_sm100.cu", "attention_pair_sm100.cu", "attention_cg2_sm100.cu", "attention_cg2p_sm100.cu", "fallthrough_f32.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "gemm_sm100.cu", "attention_sm100.cu", "attention_pair_sm100.cu", "attention_cg2_sm100.cu", "attention_cg2p_sm100.cu", "t5_attention.cu", "fallthrough_f32.cu"]
 HEADERS = [os.path.join(CSRC, "ptx.cuh"), os.path.join(CSRC, "softmax_math.cuh"), os.path.join(CSRC, "host_utils.h"), os.path.join(ROOT, "include", "wvd.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

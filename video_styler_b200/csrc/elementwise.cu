@@ -445,6 +445,86 @@ cfg_euler_kernel(const T* __restrict__ x, const T* __restrict__ vp, const T* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Keyframe editor step (diffsynth/pipelines/wan_video_editor.py:107-165, 362-390): CFG combine of the joint
+// (main | edited keyframes) velocity, velocity-field correction at the keyframe positions, Euler update of BOTH latent
+// sets -- one pass, with the reference's per-operation rounding in the tensor dtype:
+//   v      = v_nega + cfg * (v_posi - v_nega)                               (:368, three roundings; skipped without v_nega)
+//   z_diff = z_main[key_k] - z_edit[k] ; v_diff = v_main[key_k] - v_edit[k]
+//   r_k    = z_diff - v_diff * dt ; corr = alpha * r_k                      (:143-150)
+//   v_main[key_k] += corr ; v_edit[k] -= beta * corr  (beta > 0 only)       (:153-160)
+//   euler != 0: out = z + v * dsigma (flow_match.py:72-82) ; euler == 0: out = the corrected velocity
+// Velocities come as (BC, frames, HW) slabs with their own BC strides, so the concatenated (B, C, T+K, H, W) model
+// output is read in place (main part at offset 0, keyframe part at offset T*HW) and so are separate tensors.
+// frame_to_key[t] = k if main frame t is keyframe k, else -1; key_idx[k] = its main frame.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+editor_step_kernel(const T* __restrict__ z_main, const T* __restrict__ z_edit, const T* __restrict__ vp_main,
+                   const T* __restrict__ vp_edit, const T* __restrict__ vn_main, const T* __restrict__ vn_edit,
+                   long long v_main_bc_stride, long long v_edit_bc_stride, const int* __restrict__ frame_to_key,
+                   const int* __restrict__ key_idx, int bc, int t_frames, int k_frames, long long hw, float cfg, float dt,
+                   float alpha, float beta, float dsigma, int euler, T* __restrict__ out_main, T* __restrict__ out_edit) {
+    using IO = VecIO<T>;
+    constexpr int VE = IO::N;
+    const long long hwv = hw / VE;
+    const long long per_bc = static_cast<long long>(t_frames + k_frames) * hwv;
+    const long long total = per_bc * bc;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int b = static_cast<int>(i / per_bc);
+        const long long rem = i - b * per_bc;
+        const int f = static_cast<int>(rem / hwv);
+        const long long x = (rem - f * hwv) * VE;
+        const bool is_main = f < t_frames;
+        const int k = is_main ? frame_to_key[f] : f - t_frames;          // keyframe slot, -1: an ordinary main frame
+        const int t = is_main ? f : key_idx[k];                          // main frame
+        const long long zm_off = (static_cast<long long>(b) * t_frames + t) * hw + x;
+        const long long vm_off = b * v_main_bc_stride + static_cast<long long>(t) * hw + x;
+        float vm[VE], ve[VE], zm[VE], ze[VE], n[VE];
+        auto velocity = [&](const T* vp, const T* vn, long long off, float* v) {
+            IO::load(vp + off, v);
+            if (vn != nullptr) {
+                IO::load(vn + off, n);
+#pragma unroll
+                for (int e = 0; e < VE; ++e) {
+                    const float d = IO::rnd(__fsub_rn(v[e], n[e]));
+                    v[e] = IO::rnd(__fadd_rn(n[e], IO::rnd(__fmul_rn(cfg, d))));
+                }
+            }
+        };
+        velocity(vp_main, vn_main, vm_off, vm);
+        IO::load(z_main + zm_off, zm);
+        if (k >= 0) {
+            const long long ze_off = (static_cast<long long>(b) * k_frames + k) * hw + x;
+            velocity(vp_edit, vn_edit, b * v_edit_bc_stride + static_cast<long long>(k) * hw + x, ve);
+            IO::load(z_edit + ze_off, ze);
+#pragma unroll
+            for (int e = 0; e < VE; ++e) {
+                const float zd = IO::rnd(__fsub_rn(zm[e], ze[e]));
+                const float vd = IO::rnd(__fsub_rn(vm[e], ve[e]));
+                const float rk = IO::rnd(__fsub_rn(zd, IO::rnd(__fmul_rn(vd, dt))));
+                const float corr = IO::rnd(__fmul_rn(alpha, rk));
+                vm[e] = IO::rnd(__fadd_rn(vm[e], corr));
+                if (beta > 0.f) ve[e] = IO::rnd(__fsub_rn(ve[e], IO::rnd(__fmul_rn(beta, corr))));
+            }
+            if (!is_main) {
+                if (euler) {
+#pragma unroll
+                    for (int e = 0; e < VE; ++e) ve[e] = __fadd_rn(ze[e], IO::rnd(__fmul_rn(ve[e], dsigma)));
+                }
+                IO::store(out_edit + ze_off, ve);
+                continue;
+            }
+        }
+        if (euler) {
+#pragma unroll
+            for (int e = 0; e < VE; ++e) vm[e] = __fadd_rn(zm[e], IO::rnd(__fmul_rn(vm[e], dsigma)));
+        }
+        IO::store(out_main + zm_off, vm);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 gate_residual_kernel(const T* __restrict__ x, const T* __restrict__ gate, const T* __restrict__ y, T* __restrict__ out,
@@ -649,6 +729,38 @@ extern "C" __attribute__((visibility("default"))) int wvd_cfg_euler_step(const v
         ew::cfg_euler_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)v_posi, (const __nv_bfloat16*)v_nega, cfg_scale, dsigma, (__nv_bfloat16*)out, nvec);
     else
         ew::cfg_euler_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)v_posi, (const float*)v_nega, cfg_scale, dsigma, (float*)out, nvec);
+    WVD_CHECK_CUDA(cudaGetLastError());
+    return WVD_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_editor_step(
+    const void* z_main, const void* z_edit, const void* vp_main, const void* vp_edit, const void* vn_main, const void* vn_edit,
+    int64_t v_main_bc_stride, int64_t v_edit_bc_stride, const int* frame_to_key, const int* key_idx, int bc, int t_frames,
+    int k_frames, int64_t hw, float cfg_scale, float dt, float alpha, float beta, float dsigma, int euler, void* out_main,
+    void* out_edit, int dtype, wvd_stream_t stream) {
+    WVD_REQUIRE(dtype == WVD_BF16 || dtype == WVD_F32, "wvd_editor_step: bad dtype %d", dtype);
+    WVD_REQUIRE(z_main && z_edit && vp_main && vp_edit && frame_to_key && key_idx && out_main && out_edit, "wvd_editor_step: null pointer");
+    WVD_REQUIRE((vn_main == nullptr) == (vn_edit == nullptr), "wvd_editor_step: the negative branch needs both parts");
+    WVD_REQUIRE(bc > 0 && t_frames > 0 && k_frames > 0 && k_frames <= t_frames && hw > 0, "wvd_editor_step: bad sizes");
+    const int ve = dtype == WVD_BF16 ? 8 : 4;
+    WVD_REQUIRE(hw % ve == 0 && v_main_bc_stride % ve == 0 && v_edit_bc_stride % ve == 0,
+                "wvd_editor_step: H*W and the velocity strides must be multiples of %d", ve);
+    WVD_REQUIRE(v_main_bc_stride >= (int64_t)t_frames * hw && v_edit_bc_stride >= (int64_t)k_frames * hw, "wvd_editor_step: bad velocity strides");
+    WVD_REQUIRE(aligned16(z_main) && aligned16(z_edit) && aligned16(vp_main) && aligned16(vp_edit) && aligned16(vn_main) &&
+                aligned16(vn_edit) && aligned16(out_main) && aligned16(out_edit), "wvd_editor_step: pointers must be 16-byte aligned");
+    const long long total = (long long)bc * (t_frames + k_frames) * (hw / ve);
+    const unsigned grid = ew::stream_grid(total, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == WVD_BF16)
+        ew::editor_step_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+            (const __nv_bfloat16*)z_main, (const __nv_bfloat16*)z_edit, (const __nv_bfloat16*)vp_main, (const __nv_bfloat16*)vp_edit,
+            (const __nv_bfloat16*)vn_main, (const __nv_bfloat16*)vn_edit, v_main_bc_stride, v_edit_bc_stride, frame_to_key, key_idx, bc,
+            t_frames, k_frames, hw, cfg_scale, dt, alpha, beta, dsigma, euler, (__nv_bfloat16*)out_main, (__nv_bfloat16*)out_edit);
+    else
+        ew::editor_step_kernel<float><<<grid, 256, 0, st>>>(
+            (const float*)z_main, (const float*)z_edit, (const float*)vp_main, (const float*)vp_edit, (const float*)vn_main,
+            (const float*)vn_edit, v_main_bc_stride, v_edit_bc_stride, frame_to_key, key_idx, bc, t_frames, k_frames, hw, cfg_scale, dt,
+            alpha, beta, dsigma, euler, (float*)out_main, (float*)out_edit);
     WVD_CHECK_CUDA(cudaGetLastError());
     return WVD_OK;
 }

@@ -54,8 +54,10 @@ gemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __restr
             if (gn >= N) continue;
             float y = acc[i][j] + (bias ? bias[gn] : 0.f);
             if (epi == WVD_EPI_BIAS_GELU) y = gelu_tanh_f32(y);
+            if (epi == WVD_EPI_BIAS_GELU_T5) y = 0.5f * y * (1.0f + tanhf(0.7978845608028654f * (y + 0.044715f * (y * y * y))));
             if (epi == WVD_EPI_BIAS_GATE_RES) y = gate[gn] * y;
             if (epi == WVD_EPI_BIAS_RES || epi == WVD_EPI_BIAS_GATE_RES) y = res[static_cast<long long>(gm) * ldr + gn] + y;
+            if (epi == WVD_EPI_BIAS_MUL) y = y * res[static_cast<long long>(gm) * ldr + gn];
             C[static_cast<long long>(gm) * ldc + gn] = y;
         }
     }
@@ -105,8 +107,8 @@ extern "C" __attribute__((visibility("default"))) int wvd_gemm_f32(const void* A
                             const void* residual, int64_t ldr, wvd_stream_t stream) {
     WVD_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0, "wvd_gemm_f32: bad arguments");
     WVD_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "wvd_gemm_f32: dimension too large");
-    WVD_REQUIRE(epilogue >= WVD_EPI_BIAS && epilogue <= WVD_EPI_BIAS_GATE_RES, "wvd_gemm_f32: bad epilogue %d", epilogue);
-    if (epilogue == WVD_EPI_BIAS_RES || epilogue == WVD_EPI_BIAS_GATE_RES) WVD_REQUIRE(residual, "wvd_gemm_f32: residual missing");
+    WVD_REQUIRE(epilogue >= WVD_EPI_BIAS && epilogue <= WVD_EPI_BIAS_GELU_T5, "wvd_gemm_f32: bad epilogue %d", epilogue);
+    if (epilogue == WVD_EPI_BIAS_RES || epilogue == WVD_EPI_BIAS_GATE_RES || epilogue == WVD_EPI_BIAS_MUL) WVD_REQUIRE(residual, "wvd_gemm_f32: residual missing");
     if (epilogue == WVD_EPI_BIAS_GATE_RES) WVD_REQUIRE(gate, "wvd_gemm_f32: gate missing");
     dim3 grid((unsigned)((N + f32::TN - 1) / f32::TN), (unsigned)((M + f32::TM - 1) / f32::TM));
     f32::gemm_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)A, lda, (const float*)W, ldw, (const float*)bias,

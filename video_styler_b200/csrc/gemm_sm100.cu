@@ -115,18 +115,41 @@ __device__ __forceinline__ uint4 epilogue_pack8(const Params& p, const __nv_bflo
             y[q] = __floats2bfloat162_rn(gelu_tanh(yf.x), gelu_tanh(yf.y));
         }
     }
+    if (EPI == WVD_EPI_BIAS_GELU_T5) {
+        // the umT5 encoder's own GELU module: every torch op rounds to bf16 (pow, *0.044715, +x, *sqrt(2/pi), tanh, 1+, 0.5*x, *)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 yf = __bfloat1622float2(y[q]);
+            float o[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float x = e == 0 ? yf.x : yf.y;
+                const float x3 = bf16_round(x * x * x);
+                const float t1 = bf16_round(0.044715f * x3);
+                const float t2 = bf16_round(x + t1);
+                const float t3 = bf16_round(0.7978845608028654f * t2);
+                const float t4 = bf16_round(tanhf(t3));
+                const float t5 = bf16_round(1.0f + t4);
+                const float t6 = bf16_round(0.5f * x);
+                o[e] = t6 * t5;
+            }
+            y[q] = __floats2bfloat162_rn(o[0], o[1]);
+        }
+    }
     if (EPI == WVD_EPI_BIAS_GATE_RES) {
         const uint4 g = __ldg(reinterpret_cast<const uint4*>(p.gate + col));
         const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) y[q] = __hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&gw[q]), y[q]);
     }
-    if (EPI == WVD_EPI_BIAS_RES || EPI == WVD_EPI_BIAS_GATE_RES) {
+    if (EPI == WVD_EPI_BIAS_RES || EPI == WVD_EPI_BIAS_GATE_RES || EPI == WVD_EPI_BIAS_MUL) {
         uint4 r = make_uint4(0u, 0u, 0u, 0u);
         if (row_ok) r = *reinterpret_cast<const uint4*>(p.res + row * p.ldr + col);
         const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) y[q] = __hadd2_rn(*reinterpret_cast<const __nv_bfloat162*>(&rw[q]), y[q]);
+        for (int q = 0; q < 4; ++q)
+            y[q] = EPI == WVD_EPI_BIAS_MUL ? __hmul2_rn(y[q], *reinterpret_cast<const __nv_bfloat162*>(&rw[q]))
+                                           : __hadd2_rn(*reinterpret_cast<const __nv_bfloat162*>(&rw[q]), y[q]);
     }
     uint4 o;
     o.x = *reinterpret_cast<const uint32_t*>(&y[0]);
@@ -429,9 +452,9 @@ static int run(const void* A, int64_t lda, const void* const* W, int64_t ldw, co
     for (int g = 0; g < groups; ++g)
         WVD_REQUIRE(W[g] && ((uintptr_t)W[g] % 16 == 0) && (bias == nullptr || (uintptr_t)bias[g] % 16 == 0),
                     "%s: weight / bias pointers must be non-null (weights) and 16-byte aligned", who);
-    WVD_REQUIRE(epilogue >= WVD_EPI_BIAS && epilogue <= WVD_EPI_BIAS_GATE_RES, "%s: bad epilogue %d", who, epilogue);
+    WVD_REQUIRE(epilogue >= WVD_EPI_BIAS && epilogue <= WVD_EPI_BIAS_GELU_T5, "%s: bad epilogue %d", who, epilogue);
     WVD_REQUIRE(groups == 1 || epilogue == WVD_EPI_BIAS, "%s: grouped launches take the plain bias epilogue", who);
-    if (epilogue == WVD_EPI_BIAS_RES || epilogue == WVD_EPI_BIAS_GATE_RES)
+    if (epilogue == WVD_EPI_BIAS_RES || epilogue == WVD_EPI_BIAS_GATE_RES || epilogue == WVD_EPI_BIAS_MUL)
         WVD_REQUIRE(residual && ldr % 8 == 0 && ldr >= N, "%s: residual epilogue needs residual/ldr", who);
     if (epilogue == WVD_EPI_BIAS_GATE_RES) WVD_REQUIRE(gate, "%s: gate epilogue needs gate", who);
     // developer experiments: bits 8..15 of `variant` override the rasterisation band width (0 = heuristic)
@@ -482,6 +505,8 @@ static int run(const void* A, int64_t lda, const void* const* W, int64_t ldw, co
         WVD_GEMM_CASE(WVD_EPI_BIAS_GELU)
         WVD_GEMM_CASE(WVD_EPI_BIAS_RES)
         WVD_GEMM_CASE(WVD_EPI_BIAS_GATE_RES)
+        WVD_GEMM_CASE(WVD_EPI_BIAS_MUL)
+        WVD_GEMM_CASE(WVD_EPI_BIAS_GELU_T5)
         default: return set_error(WVD_ERR_INVALID, "%s: bad epilogue %d", who, epilogue);
     }
 #undef WVD_GEMM_CASE

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_RES, WVD_BF16, WVD_F32, WvdError, check
+from ._lib import EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_GELU_T5, EPI_BIAS_MUL, EPI_BIAS_RES, WVD_BF16, WVD_F32, WvdError, check
 
 Tensor = torch.Tensor
 
@@ -384,3 +384,86 @@ def attention_scatter(q: Tensor, k: Tensor, v: Tensor, num_heads: int, out_ptrs,
     if prof:
         e1.record()
         PROFILE.setdefault("self_attention", []).append((e0, e1, num_heads, sq))
+
+
+def attention_bias(q: Tensor, k: Tensor, v: Tensor, num_heads: int, bias: Optional[Tensor] = None,
+                   key_mask: Optional[Tensor] = None, scale: float = 1.0, out: Optional[Tensor] = None) -> Tensor:
+    """softmax(q k^T * scale + bias[h][j - i]; masked keys -> finfo.min) v for head_dim 64 -- the umT5 encoder's
+    self-attention (wan_video_text_encoder.py:55-90).  q (Lq, H*64), k / v (Lk, H*64) views; bias (H, Lq + Lk - 1) in the
+    activation dtype, indexed by (j - i) + Lq - 1; key_mask int32 (Lk,), 0 = masked."""
+    q, k, v = _chk2d(q, "q"), _chk2d(k, "k"), _chk2d(v, "v")
+    lq, width = q.shape
+    lk = k.shape[0]
+    if width != num_heads * 64 or k.shape[1] != width or v.shape != k.shape or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise WvdError(f"attention_bias: head_dim must be 64 and q/k/v consistent (q {tuple(q.shape)}, k {tuple(k.shape)}, heads {num_heads})")
+    if bias is not None:
+        bias = _chk2d(bias, "bias")
+        if bias.shape[0] != num_heads or bias.shape[1] < lq + lk - 1 or bias.dtype != q.dtype:
+            raise WvdError(f"attention_bias: bias must be ({num_heads}, >= {lq + lk - 1}) {q.dtype}, got {tuple(bias.shape)} {bias.dtype}")
+    if key_mask is not None:
+        key_mask = key_mask.reshape(-1)
+        if key_mask.numel() != lk or key_mask.dtype != torch.int32 or not key_mask.is_cuda or key_mask.stride(0) != 1:
+            raise WvdError("attention_bias: key_mask must be a contiguous int32 CUDA vector of length Lk")
+    if out is None:
+        out = torch.empty((lq, width), dtype=q.dtype, device=q.device)
+    _chk2d(out, "out")
+    if lq == 0:
+        return out
+    if lk == 0:
+        raise WvdError("attention_bias: empty key/value sequence")
+    check(_lib.load().wvd_attention_bias_fwd(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), _p(bias),
+                                             _ld(bias) if bias is not None else 0, _p(key_mask), out.data_ptr(), _ld(out),
+                                             num_heads, lq, lk, 64, float(scale), _dt(q), _stream()), "wvd_attention_bias_fwd")
+    return out
+
+
+def editor_step(z_main: Tensor, z_edit: Tensor, v_posi, v_nega, frame_to_key: Tensor, key_idx: Tensor, cfg_scale: float,
+                dt: float, alpha: float, beta: float, dsigma: float = 0.0, euler: bool = True):
+    """The keyframe editor's per-step arithmetic in one kernel (wan_video_editor.py:107-165, 362-390).
+
+    z_main (B, C, T, H, W), z_edit (B, C, K, H, W); v_posi / v_nega: either the joint (B, C, T+K, H, W) model output or a
+    (v_main, v_edit) pair of separate tensors; v_nega None = no CFG.  Returns the new (z_main, z_edit) for ``euler``,
+    else the corrected (v_main, v_edit)."""
+    b, c, t, h, w = z_main.shape
+    kf = z_edit.shape[2]
+    if z_edit.shape != (b, c, kf, h, w) or z_edit.dtype != z_main.dtype:
+        raise WvdError("editor_step: z_edit must be (B, C, K, H, W) of z_main's dtype")
+    for name, x in (("z_main", z_main), ("z_edit", z_edit)):
+        if not x.is_cuda or not x.is_contiguous():
+            raise WvdError(f"editor_step: {name} must be a contiguous CUDA tensor (there is no CPU fallback)")
+    hw = h * w
+
+    def parts(v, name):
+        if v is None:
+            return None, None, 0, 0
+        if isinstance(v, (tuple, list)):
+            vm, ve = v
+            if vm.shape != z_main.shape or ve.shape != z_edit.shape:
+                raise WvdError(f"editor_step: {name} pair must match z_main / z_edit")
+            tensors, strides = (vm, ve), (t * hw, kf * hw)
+        else:
+            if v.shape != (b, c, t + kf, h, w):
+                raise WvdError(f"editor_step: {name} must be the joint (B, C, T+K, H, W) velocity, got {tuple(v.shape)}")
+            tensors, strides = (v, v), ((t + kf) * hw, (t + kf) * hw)
+        for x in tensors:
+            if not x.is_cuda or not x.is_contiguous() or x.dtype != z_main.dtype:
+                raise WvdError(f"editor_step: {name} must be contiguous CUDA tensors of z_main's dtype")
+        if tensors[0] is tensors[1]:
+            return v.data_ptr(), v.data_ptr() + t * hw * v.element_size(), strides[0], strides[1]
+        return tensors[0].data_ptr(), tensors[1].data_ptr(), strides[0], strides[1]
+
+    pm, pe, sm, se = parts(v_posi, "v_posi")
+    nm, ne, sm2, se2 = parts(v_nega, "v_nega")
+    if pm is None:
+        raise WvdError("editor_step: v_posi is required")
+    if nm is not None and (sm2, se2) != (sm, se):
+        raise WvdError("editor_step: v_posi and v_nega must have the same layout")
+    for name, x, n in (("frame_to_key", frame_to_key, t), ("key_idx", key_idx, kf)):
+        if x.dtype != torch.int32 or not x.is_cuda or x.numel() != n or not x.is_contiguous():
+            raise WvdError(f"editor_step: {name} must be a contiguous int32 CUDA vector of length {n}")
+    out_main, out_edit = torch.empty_like(z_main), torch.empty_like(z_edit)
+    check(_lib.load().wvd_editor_step(z_main.data_ptr(), z_edit.data_ptr(), pm, pe, nm, ne, sm, se, frame_to_key.data_ptr(),
+                                      key_idx.data_ptr(), b * c, t, kf, hw, float(cfg_scale), float(dt), float(alpha), float(beta),
+                                      float(dsigma), 1 if euler else 0, out_main.data_ptr(), out_edit.data_ptr(), _dt(z_main),
+                                      _stream()), "wvd_editor_step")
+    return out_main, out_edit
