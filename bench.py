@@ -35,12 +35,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "wan_vace_14b_dit_s_per_denoise_step_832x480x73"
+NCU_ATTENTION_SUMMARY = "r2_attention_cg2p_c3.txt"       # ncu --set full of the dominant kernel (tools/ncu_summary.py)
 
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE self-attention launch at c3, from the committed
     `ncu --set full` capture summary (profiles/, written by tools/ncu_summary.py).  None if the summary is absent."""
-    p = os.path.join(ROOT, "profiles", "r1_attention_pair_c3.txt")
+    p = os.path.join(ROOT, "profiles", NCU_ATTENTION_SUMMARY)
     if not os.path.exists(p):
         return None
     tot, mult = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -237,6 +238,64 @@ def gpu_reference_leg(dit, vace, devin, t_dev, ours_out, ours_ms, size, reps=3):
     return res
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# The callers either side of the DiT, timed in the same run: one umT5-XXL prompt (24 layers,
+# 512 tokens, bf16) on this path and as the oracle's restatement with torch eager on the same GPU (cuBLAS + eager
+# softmax / norms: the reference's kernel sequence), and the keyframe editor's per-step arithmetic at the c3 latent
+# size (fused kernel vs the reference's torch op sequence; HBM-bound: bytes = 4 x (T + K) frames).
+# ----------------------------------------------------------------------------------------------------------------
+def aux_leg(dev, hbm_gbs):
+    import torch
+    from oracle import aux_oracle as A
+    from video_styler_b200 import ops, wan_video_editor as E, wan_video_text_encoder as T
+
+    def timed(fn, iters, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    res = {}
+    try:
+        with torch.no_grad():
+            cfg = dict(A.T5_CONFIGS["umt5-xxl"]); cfg["vocab"] = 4096          # the embedding table is a gather, kept small
+            sd = A.make_t5_state_dict(cfg, seed=0, dtype=torch.bfloat16, device=dev)
+            enc = T.WanTextEncoder(**cfg).eval().requires_grad_(False)
+            enc.load_state_dict(sd, strict=True)
+            enc = enc.to(device=dev, dtype=torch.bfloat16)
+            ids, mask = (t.to(dev) for t in A.make_t5_inputs(cfg, 512, 77, seed=1))
+            ms = timed(lambda: T.encode_prompt(enc, ids, mask), 10)
+            ms_ref = timed(lambda: A.encode_prompt(sd, cfg, ids, mask), 5)
+            l, d, da, f, nl = 512, cfg["dim"], cfg["dim_attn"], cfg["dim_ffn"], cfg["num_layers"]
+            flops = nl * (2 * l * (4 * d * da + 3 * d * f) + 4 * l * l * da)
+            res["umt5_xxl_prompt"] = dict(wvd_ms=ms, torch_eager_ms=ms_ref, speedup=ms_ref / ms, tflop=flops / 1e12,
+                                          wvd_tflops_per_s=flops / ms / 1e9,
+                                          what="24 layers, dim 4096, 64 heads x 64, ffn 10240, 512 tokens (77 valid), bf16, batch 1")
+            del enc, sd
+            torch.cuda.empty_cache()
+            g = torch.Generator(device=dev).manual_seed(9)
+            keys = [0, 4, 9, 14, 18]
+            r = lambda *s: torch.randn(*s, device=dev, generator=g).bfloat16()      # noqa: E731
+            zm, ze, vp, vn = r(1, 16, 19, 60, 104), r(1, 16, 5, 60, 104), r(1, 16, 24, 60, 104), r(1, 16, 24, 60, 104)
+            km = E.KeyframeMap(19, keys, dev)
+            us = 1e3 * timed(lambda: ops.editor_step(zm, ze, vp, vn, km.frame_to_key, km.key_idx, 5.0, 19.5, 10.0, 0.0, -0.0123), 200, 10)
+            us_ref = 1e3 * timed(lambda: A.editor_step(zm, ze, vp, vn, keys, 5.0, 19.5, 10.0, 0.0, -0.0123), 50, 5)
+            nbytes = 4 * vp.numel() * 2
+            res["editor_step_c3"] = dict(wvd_us=us, torch_ops_us=us_ref, speedup=us_ref / us, algorithmic_bytes=nbytes,
+                                         wvd_gb_per_s=nbytes / us / 1e3, hbm_peak_gb_per_s=hbm_gbs,
+                                         what="(1,16,19,60,104) main + 5 keyframe latents: CFG + velocity correction + Euler of both sets "
+                                              "in one kernel, bf16; 9.6 MB of traffic = L2-resident and launch-latency bound")
+    except Exception as e:          # noqa: BLE001 -- an extra leg must not take the bench down
+        res["unavailable"] = repr(e)[:200]
+    return res
+
+
 def exchange_kind():
     from video_styler_b200 import ulysses
     kinds = {("UlyssesExchange" if getattr(e, "_nccl_only", False) else type(e).__name__) for e in ulysses._EXCHANGES.values()}
@@ -263,6 +322,7 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the torch-eager (cuBLAS + SDPA / FA2) leg")
     ap.add_argument("--no-loop", action="store_true", help="skip the CFG-step (denoise loop) timing, plain vs fused")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the untimed sharded-vs-unsharded check")
+    ap.add_argument("--no-aux", action="store_true", help="skip the umT5 prompt / keyframe-editor step timings (SURVEY 8(f)3-4)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -422,6 +482,9 @@ def main():
                 gpu_c1[nm + "_s"] = timed(f1, 10) / 1e3
                 del d1
 
+    aux = None
+    if world == 1 and not args.no_aux:
+        aux = aux_leg(dev, peaks()["hbm"])
     if rank == 0:
         pk = peaks()
         att_ms = sum(att) / max(1, len(att))
@@ -446,7 +509,7 @@ def main():
                                   achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s",
                                   frac=(achieved / pk["bf16_sustained"]) if achieved else None,
                                   traffic=ncu_traffic_bytes() if args.workload == "c3" and world == 1 else None,
-                                  traffic_unit="bytes per launch (dram read + write, ncu --set full, profiles/r1_attention_pair_c3.txt); "
+                                  traffic_unit=f"bytes per launch (dram read + write, ncu --set full, profiles/{NCU_ATTENTION_SUMMARY}); "
                                                "algorithmic minimum 4*A = 1.214e9 (q, k, v read + out written once)",
                                   peak_source=f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
                                   launches_timed=len(att), avg_launch_ms=att_ms,
@@ -460,6 +523,8 @@ def main():
             line["denoise_loop"] = loop
         if gpu_ref is not None:
             line["gpu_reference"] = gpu_ref
+        if aux is not None:
+            line["aux"] = aux
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_entry(S.model_flops("14B", 29640, True))
             if gpu_c1 is not None:
