@@ -291,6 +291,37 @@ def aux_leg(dev, hbm_gbs):
                                          wvd_gb_per_s=nbytes / us / 1e3, hbm_peak_gb_per_s=hbm_gbs,
                                          what="(1,16,19,60,104) main + 5 keyframe latents: CFG + velocity correction + Euler of both sets "
                                               "in one kernel, bf16; 9.6 MB of traffic = L2-resident and launch-latency bound")
+            # VAE tile blending at the c3 video size: 9 decoded tiles of (1, 3, 73, 240, 416) into (1, 3, 73, 480, 832)
+            from video_styler_b200 import wan_video_vae as VA
+            tasks = VA.tile_tasks(60, 104, (30, 52), (15, 26))
+            tiles = [torch.randn(1, 3, 73, 240, 416, device=dev, generator=g).bfloat16() for _ in range(3)]
+            values = torch.zeros(1, 3, 73, 480, 832, device=dev, dtype=torch.bfloat16)
+            weight = torch.zeros(480, 832, device=dev, dtype=torch.bfloat16)
+            bounds = [(h == 0, h_ >= 60, w == 0, w_ >= 104) for h, h_, w, w_ in tasks]
+
+            def blend_wvd():
+                values.zero_(); weight.zero_()
+                for i, (h, _, w, _) in enumerate(tasks):
+                    ops.tile_blend(values, weight, tiles[i % 3], h * 8, w * 8, bounds[i], (120, 208))
+                ops.tile_finalize(values, weight, (-1.0, 1.0))
+
+            def blend_torch(vals, wgt, tl, dv):
+                vals.zero_(); wgt.zero_()
+                for i, (h, _, w, _) in enumerate(tasks):
+                    t_ = tl[i % 3]
+                    mask = A.vae_build_mask(t_, bounds[i], (120, 208)).to(dtype=vals.dtype, device=dv)
+                    vals[:, :, :, h * 8:h * 8 + 240, w * 8:w * 8 + 416] += t_ * mask
+                    wgt[:, :, :, h * 8:h * 8 + 240, w * 8:w * 8 + 416] += mask
+                return (vals / wgt).clamp_(-1, 1)
+            w5 = torch.zeros(1, 1, 73, 480, 832, device=dev, dtype=torch.bfloat16)
+            ms_b = timed(blend_wvd, 10)
+            ms_bt = timed(lambda: blend_torch(values, w5, tiles, dev), 5)
+            nbytes = len(tasks) * 3 * tiles[0].numel() * 2 + 2 * values.numel() * 2
+            res["vae_tile_blend_c3"] = dict(wvd_ms=ms_b, torch_ops_on_gpu_ms=ms_bt, speedup=ms_bt / ms_b, algorithmic_bytes=nbytes,
+                                            wvd_gb_per_s=nbytes / ms_b / 1e6, hbm_peak_gb_per_s=hbm_gbs,
+                                            what="9 tiles (1,3,73,240,416) blended into (1,3,73,480,832) + normalise + clamp, bf16; bytes = "
+                                                 "per tile (read tile + read / write the window) + the final pass; the reference does "
+                                                 "this on the CPU with a PCIe copy per tile (wan_video_vae.py:1118)")
     except Exception as e:          # noqa: BLE001 -- an extra leg must not take the bench down
         res["unavailable"] = repr(e)[:200]
     return res

@@ -89,6 +89,18 @@ int wvd_scale_add(const void* x, const void* y, float scale, void* out, int64_t 
  * reference's eager expressions.  v_nega == NULL (cfg_scale == 1): out = x + v_posi * dsigma.  out may alias x.     */
 int wvd_cfg_euler_step(const void* x, const void* v_posi, const void* v_nega, float cfg_scale, float dsigma, void* out,
                        int64_t n_elems, int dtype, wvd_stream_t stream);
+/* ---- VAE tile blending (WanVideoVAE.tiled_decode / tiled_encode, wan_video_vae.py:1081-1204) -----------------------
+ * wvd_tile_blend: values[pl, y0:y0+th, x0:x0+tw] += tile[pl] * mask and weight[y0:.., x0:..] += mask for `planes` =
+ * channels x frames planes of H x W (weight is ONE H x W plane: the mask does not depend on channel or frame).
+ * mask = min(ramp_h, ramp_w) with the reference's linear ramps of `border_*` pixels on the sides that are not volume
+ * boundaries; `bounds` bit 0 = top, 1 = bottom, 2 = left, 3 = right is a boundary.  wvd_tile_finalize: values /= weight
+ * (clamped to [lo, hi] if clamp != 0).  Reference rounding per operation in `dtype`; everything stays in HBM (the
+ * reference accumulates on the CPU).                                                                               */
+int wvd_tile_blend(void* values, void* weight, const void* tile, int planes, int H, int W, int th, int tw, int y0, int x0,
+                   int bounds, int border_h, int border_w, int dtype, wvd_stream_t stream);
+int wvd_tile_finalize(void* values, const void* weight, int planes, int64_t hw, int clamp, float lo, float hi, int dtype,
+                      wvd_stream_t stream);
+
 /* ---- Keyframe editor step (wan_video_editor.py:107-165 compute_velocity_correction, :362-390 CFG + split + Euler) ----
  * One pass over the main latents (BC, T, HW) and the edited-keyframe latents (BC, K, HW): CFG combine (v_nega may be
  * NULL), velocity correction at the keyframe positions (alpha, beta, dt as in the reference), then either the Euler

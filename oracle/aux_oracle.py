@@ -175,3 +175,95 @@ def make_editor_inputs(shape=(1, 16, 7, 8, 12), keyframes=(0, 3, 6), seed=5, dty
     k = len(keyframes)
     r = lambda *s: torch.randn(*s, generator=g).to(dtype)      # noqa: E731
     return dict(z_main=r(b, c, t, h, w), z_edit=r(b, c, k, h, w), v_posi=r(b, c, t + k, h, w), v_nega=r(b, c, t + k, h, w))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VAE tiling layer (wan_video_vae.py:1081-1248) around a stand-in convolutional model
+# ---------------------------------------------------------------------------------------------------------------
+class ToyVAEModel:
+    """Stand-in for ``VideoVAE_`` (wan_video_vae.py:951-1056) with its shape contract -- decode (1, 16, T, h, w) ->
+    (1, 3, 4T - 3, 8h, 8w), encode (1, 3, T, H, W) -> (1, 16, (T + 3) // 4, H / 8, W / 8) -- cheap, deterministic, and
+    dependent on the position INSIDE the tile, so that overlapping tiles disagree and the blending matters.  The tiling
+    layer under test never looks inside the model; the real one cannot travel to the GPU box."""
+
+    def decode(self, z, scale):
+        x = 1.5 * (z[:, 0:3] * 0.6 + z[:, 3:6] * 0.3 - z[:, 6:9] * 0.2)
+        x = x.repeat_interleave(4, dim=2)[:, :, 3:].repeat_interleave(8, dim=3).repeat_interleave(8, dim=4)
+        hh, ww = x.shape[3], x.shape[4]
+        ry = torch.linspace(0, 1, hh, device=x.device).view(1, 1, 1, hh, 1)
+        rx = torch.linspace(0, 1, ww, device=x.device).view(1, 1, 1, 1, ww)
+        return (x + (0.2 * ry - 0.1 * rx).to(x.dtype)).to(z.dtype)
+
+    def encode(self, x, scale):
+        y = torch.nn.functional.avg_pool3d(x[:, :, ::4].float(), (1, 8, 8)).to(x.dtype)          # (1, 3, (T+3)//4, H/8, W/8)
+        mix = torch.stack([y[:, i % 3] * (0.3 + 0.1 * i) - y[:, (i + 1) % 3] * 0.05 * i for i in range(16)], dim=1)
+        hh, ww = mix.shape[3], mix.shape[4]
+        ry = torch.linspace(0, 1, hh, device=x.device).view(1, 1, 1, hh, 1)
+        rx = torch.linspace(0, 1, ww, device=x.device).view(1, 1, 1, 1, ww)
+        return (mix + (0.1 * ry + 0.2 * rx).to(mix.dtype)).to(x.dtype)
+
+
+def vae_build_1d_mask(length, left_bound, right_bound, border_width):
+    """WanVideoVAE.build_1d_mask (:1081-1087)."""
+    x = torch.ones((length,))
+    if not left_bound:
+        x[:border_width] = (torch.arange(border_width) + 1) / border_width
+    if not right_bound:
+        x[-border_width:] = torch.flip((torch.arange(border_width) + 1) / border_width, dims=(0,))
+    return x
+
+
+def vae_build_mask(data, is_bound, border_width):
+    """WanVideoVAE.build_mask (:1090-1100)."""
+    hh, ww = data.shape[3], data.shape[4]
+    h = vae_build_1d_mask(hh, is_bound[0], is_bound[1], border_width[0]).view(hh, 1).expand(hh, ww)
+    w = vae_build_1d_mask(ww, is_bound[2], is_bound[3], border_width[1]).view(1, ww).expand(hh, ww)
+    return torch.stack([h, w]).min(dim=0).values.view(1, 1, 1, hh, ww)
+
+
+def vae_tiled(model, source, tile_size, tile_stride, mode, z_dim=16, factor=8, scale=None):
+    """WanVideoVAE.tiled_decode (:1103-1153) / tiled_encode (:1155-1204) on ``source``'s own device."""
+    _, _, t, hgt, wid = source.shape
+    (size_h, size_w), (stride_h, stride_w) = tile_size, tile_stride
+    tasks = []
+    for h in range(0, hgt, stride_h):
+        if h - stride_h >= 0 and h - stride_h + size_h >= hgt:
+            continue
+        for w in range(0, wid, stride_w):
+            if w - stride_w >= 0 and w - stride_w + size_w >= wid:
+                continue
+            tasks.append((h, h + size_h, w, w + size_w))
+    if mode == "decode":
+        out_t, oh, ow, ch = t * 4 - 3, hgt * factor, wid * factor, 3
+        border = ((size_h - stride_h) * factor, (size_w - stride_w) * factor)
+        pos = lambda v: v * factor           # noqa: E731
+    else:
+        out_t, oh, ow, ch = (t + 3) // 4, hgt // factor, wid // factor, z_dim
+        border = ((size_h - stride_h) // factor, (size_w - stride_w) // factor)
+        pos = lambda v: v // factor          # noqa: E731
+    weight = torch.zeros((1, 1, out_t, oh, ow), dtype=source.dtype, device=source.device)
+    values = torch.zeros((1, ch, out_t, oh, ow), dtype=source.dtype, device=source.device)
+    for h, h_, w, w_ in tasks:
+        tile = source[:, :, :, h:h_, w:w_]
+        tile = model.decode(tile, scale) if mode == "decode" else model.encode(tile, scale)
+        mask = vae_build_mask(tile, (h == 0, h_ >= hgt, w == 0, w_ >= wid), border).to(dtype=source.dtype, device=source.device)
+        th, tw = pos(h), pos(w)
+        values[:, :, :, th:th + tile.shape[3], tw:tw + tile.shape[4]] += tile * mask
+        weight[:, :, :, th:th + tile.shape[3], tw:tw + tile.shape[4]] += mask
+    values = values / weight
+    return values.clamp_(-1, 1) if mode == "decode" else values
+
+
+VAE_CASES = {
+    # name: (mode, source shape, tile_size, tile_stride) -- tile sizes in the units the reference's tiled_* methods take
+    "decode_small": ("decode", (1, 16, 3, 9, 13), (4, 6), (2, 3)),
+    "decode_ragged": ("decode", (1, 16, 2, 7, 10), (4, 4), (3, 2)),
+    "decode_one_tile": ("decode", (1, 16, 2, 4, 4), (34, 34), (18, 16)),
+    "encode_small": ("encode", (1, 3, 9, 72, 104), (32, 48), (16, 24)),
+    "encode_odd": ("encode", (1, 3, 5, 56, 88), (40, 40), (24, 16)),
+}
+
+
+def make_vae_source(shape, seed=11, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g).to(dtype)

@@ -1,5 +1,5 @@
 """Golden fixtures of the umT5 encoder and the keyframe-editor arithmetic from the REAL reference (build container
-only)  --  TEST INFRASTRUCTURE.      python oracle/make_golden_aux.py      # writes tests/golden/{t5_tiny,t5_small,editor_step}.pt
+only)  --  TEST INFRASTRUCTURE.      python oracle/make_golden_aux.py      # writes tests/golden/{t5_tiny,t5_small,editor_step,vae_tiling}.pt
 
 Loads the synthetic state dict with strict=True into the real ``WanTextEncoder`` (pins the key names), runs its forward
 in fp32 on CPU; calls the real ``WanVideoEditorPipeline`` methods (compute_velocity_correction, construct_rope_ids,
@@ -63,5 +63,28 @@ def main():
     print("editor_step:", {k_: float(v_["z_main_next"].abs().mean()) for k_, v_ in cases.items()})
 
 
+
+
+def vae_goldens():
+    """The REAL WanVideoVAE tiling methods (tiled_decode / tiled_encode, on the CPU as the reference runs them) around the
+    stand-in model, fp32 and bf16."""
+    ref_shim.load()
+    V = importlib.import_module("diffsynth.models.wan_video_vae")
+    vae = object.__new__(V.WanVideoVAE)
+    torch.nn.Module.__init__(vae)
+    vae.model, vae.upsampling_factor, vae.z_dim = A.ToyVAEModel(), 8, 16
+    vae.scale = [torch.zeros(16), torch.ones(16)]
+    out = {}
+    for name, (mode, shape, size, stride) in A.VAE_CASES.items():
+        for dt in (torch.float32, torch.bfloat16):
+            src = A.make_vae_source(shape, dtype=dt)
+            with torch.no_grad():
+                res = vae.tiled_decode(src, "cpu", size, stride) if mode == "decode" else vae.tiled_encode(src, "cpu", size, stride)
+            out[(name, str(dt))] = res.clone()
+        print(f"vae {name}: {tuple(res.shape)} |x| {float(res.float().abs().mean()):.4f}")
+    torch.save(dict(cases=out, seed=11, torch_version=torch.__version__), os.path.join(OUT, "vae_tiling.pt"))
+
+
 if __name__ == "__main__":
     main()
+    vae_goldens()

@@ -146,3 +146,18 @@ def ulysses_unpack_out(recv, heads, world, out=None):
     p, n, w = recv.shape
     y = recv.permute(1, 0, 2).reshape(n, p * w)
     return _ret(y, out)
+
+
+def tile_blend(values, weight, tile, y0, x0, is_bound, border_width):
+    from oracle import aux_oracle as A
+    mask = A.vae_build_mask(tile, is_bound, border_width).to(values.dtype)
+    th, tw = tile.shape[3], tile.shape[4]
+    values[:, :, :, y0:y0 + th, x0:x0 + tw] += tile * mask
+    weight[y0:y0 + th, x0:x0 + tw] += mask[0, 0, 0]
+
+
+def tile_finalize(values, weight, clamp=None):
+    values.copy_(values / weight)
+    if clamp is not None:
+        values.clamp_(clamp[0], clamp[1])
+    return values

@@ -125,3 +125,32 @@ def test_edit_denoise_loop_host_logic():
             dt = float(sch.timesteps[i] - sch.timesteps[i + 1]) if i < steps - 1 else 0.0
             rm, re_ = A.editor_step(rm, re_, vp, vn, keys, cfg_scale, dt, alpha, beta, sch.dsigma(ts))
     assert O.parity_metrics(zm, rm)["rel_l2"] <= 1e-5 and O.parity_metrics(ze, re_)["rel_l2"] <= 1e-5
+
+
+# ---- VAE tiling layer (the tiling part) ----
+@pytest.mark.parametrize("name", ["decode_small", "decode_ragged", "decode_one_tile", "encode_small", "encode_odd"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_vae_tiling_oracle_and_host_logic_match_the_real_reference(golden_dir, name, dtype):
+    """The oracle's restatement AND the package's TiledVAE (through the CPU stand-in of the two kernels) reproduce the REAL
+    WanVideoVAE.tiled_decode / tiled_encode bit for bit, fp32 and bf16 (same tile enumeration, masks, rounding)."""
+    from video_styler_b200 import wan_video_vae as VA
+    fix = _load(golden_dir, "vae_tiling")
+    mode, shape, size, stride = A.VAE_CASES[name]
+    src = A.make_vae_source(shape, seed=fix["seed"], dtype=dtype)
+    gold = fix["cases"][(name, str(dtype))]
+    with torch.no_grad():
+        assert torch.equal(A.vae_tiled(A.ToyVAEModel(), src, size, stride, mode), gold)
+        t = VA.TiledVAE(A.ToyVAEModel(), ops=cpu_backend)
+        out = t.tiled_decode(src, "cpu", size, stride) if mode == "decode" else t.tiled_encode(src, "cpu", size, stride)
+    assert torch.equal(out, gold)
+
+
+def test_vae_masks_and_errors():
+    from video_styler_b200 import wan_video_vae as VA
+    t = VA.TiledVAE(A.ToyVAEModel(), ops=cpu_backend)
+    data = torch.zeros(1, 3, 2, 12, 20)
+    for bound in [(True, True, True, True), (False, True, True, False), (False, False, False, False)]:
+        assert torch.equal(t.build_mask(data, bound, (5, 8)), A.vae_build_mask(data, bound, (5, 8)))
+    assert VA.tile_tasks(9, 13, (4, 6), (2, 3)) == [(h, h + 4, w, w + 6) for h in (0, 2, 4, 6) for w in (0, 3, 6, 9)]
+    with pytest.raises(WvdError):                    # CPU tensors on the product path: no fallback
+        VA.TiledVAE(A.ToyVAEModel()).tiled_decode(torch.zeros(1, 16, 2, 8, 8), "cpu", (4, 4), (2, 2))

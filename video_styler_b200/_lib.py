@@ -24,6 +24,8 @@ SIGNATURES = {
                             c_int, c_void_p],
     "wvd_scale_add": [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p],
     "wvd_cfg_euler_step": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_int64, c_int, c_void_p],
+    "wvd_tile_blend": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "wvd_tile_finalize": [c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_float, c_int, c_void_p],
     "wvd_editor_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int,
                         c_int, c_int, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "wvd_attention_bias_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,

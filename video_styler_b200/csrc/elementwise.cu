@@ -42,6 +42,8 @@ template <> struct VecIO<__nv_bfloat16> {
         *reinterpret_cast<uint4*>(p) = u;
     }
     static __device__ __forceinline__ float rnd(float x) { return bf16_round(x); }
+    static __device__ __forceinline__ float ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    static __device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
 template <> struct VecIO<float> {
@@ -63,6 +65,8 @@ template <> struct VecIO<float> {
         *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
     }
     static __device__ __forceinline__ float rnd(float x) { return x; }
+    static __device__ __forceinline__ float ld1(const float* p) { return *p; }
+    static __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
 };
 
 // Opaque to the optimiser: stops it from keeping the unpacked fp32 copy of a packed row alive across passes
@@ -525,6 +529,86 @@ editor_step_kernel(const T* __restrict__ z_main, const T* __restrict__ z_edit, c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// VAE tile blending (WanVideoVAE.tiled_decode / tiled_encode, diffsynth/models/wan_video_vae.py:1081-1204):
+//   values[:, :, :, y0:y0+th, x0:x0+tw] += tile * mask ; weight[..., same window] += mask ; finally values / weight (clamped
+//   for decode).  mask[y][x] = min(ramp_h(y), ramp_w(x)), ramp = 1 inside, (i + 1) / border over the first `border`
+//   pixels of a side that is not a volume boundary (the right / bottom ramp wins where the two overlap, like the
+//   reference's two slice assignments), evaluated in fp32 and rounded to the tensor dtype; products and sums round per
+//   operation like the reference's tensor ops.  The reference keeps `values` / `weight` on the CPU and ships every tile
+//   over PCIe; here both stay in HBM.  The weight is the same for every channel and frame: one (H, W) plane.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tile_ramp(int i, int n, bool lo_bound, bool hi_bound, int border) {
+    const int r = n - 1 - i;
+    if (!hi_bound && r < border) return __fdiv_rn(static_cast<float>(r + 1), static_cast<float>(border));
+    if (!lo_bound && i < border) return __fdiv_rn(static_cast<float>(i + 1), static_cast<float>(border));
+    return 1.0f;
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+tile_blend_kernel(T* __restrict__ values, T* __restrict__ weight, const T* __restrict__ tile, int planes, int H, int W, int th,
+                  int tw, int y0, int x0, int bounds, int border_h, int border_w) {
+    using IO = VecIO<T>;
+    // 32-bit index arithmetic (the launcher guarantees planes * th * tw < 2^31): 64-bit div / mod per element cost more
+    // than the memory traffic of this kernel
+    const unsigned twv = tw / V;
+    const unsigned total = static_cast<unsigned>(planes) * th * twv;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned rest = i / twv;
+        const int xv = static_cast<int>(i - rest * twv);
+        const int pl = static_cast<int>(rest / th);               // channel * frames + frame
+        const int y = static_cast<int>(rest - pl * th);
+        const int x = xv * V;
+        const float mh = tile_ramp(y, th, bounds & 1, bounds & 2, border_h);
+        const long long src = (static_cast<long long>(pl) * th + y) * tw + x;
+        const long long dst = (static_cast<long long>(pl) * H + y0 + y) * W + x0 + x;
+        const long long wdst = static_cast<long long>(y0 + y) * W + x0 + x;
+        float t[V], a[V], w[V], m[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) m[e] = IO::rnd(fminf(mh, tile_ramp(x + e, tw, bounds & 4, bounds & 8, border_w)));
+        if (V == 1) {
+            t[0] = IO::ld1(tile + src); a[0] = IO::ld1(values + dst);
+            IO::st1(values + dst, __fadd_rn(a[0], IO::rnd(__fmul_rn(t[0], m[0]))));
+            if (pl == 0) IO::st1(weight + wdst, __fadd_rn(IO::ld1(weight + wdst), m[0]));
+        } else {
+            IO::load(tile + src, t);
+            IO::load(values + dst, a);
+#pragma unroll
+            for (int e = 0; e < V; ++e) a[e] = __fadd_rn(a[e], IO::rnd(__fmul_rn(t[e], m[e])));
+            IO::store(values + dst, a);
+            if (pl == 0) {
+                IO::load(weight + wdst, w);
+#pragma unroll
+                for (int e = 0; e < V; ++e) w[e] = __fadd_rn(w[e], m[e]);
+                IO::store(weight + wdst, w);
+            }
+        }
+    }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+tile_finalize_kernel(T* __restrict__ values, const T* __restrict__ weight, int planes, long long hw, int clamp, float lo, float hi) {
+    using IO = VecIO<T>;
+    const long long hwv = hw / V;
+    const long long total = planes * hwv;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long p = (i % hwv) * V;
+        float a[V], w[V];
+        if (V == 1) { a[0] = IO::ld1(values + i); w[0] = IO::ld1(weight + p); }
+        else { IO::load(values + i * V, a); IO::load(weight + p, w); }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            a[e] = IO::rnd(__fdiv_rn(a[e], w[e]));
+            if (clamp) a[e] = fminf(fmaxf(a[e], lo), hi);
+        }
+        if (V == 1) IO::st1(values + i, a[0]);
+        else IO::store(values + i * V, a);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 gate_residual_kernel(const T* __restrict__ x, const T* __restrict__ gate, const T* __restrict__ y, T* __restrict__ out,
@@ -761,6 +845,47 @@ extern "C" __attribute__((visibility("default"))) int wvd_editor_step(
             (const float*)z_main, (const float*)z_edit, (const float*)vp_main, (const float*)vp_edit, (const float*)vn_main,
             (const float*)vn_edit, v_main_bc_stride, v_edit_bc_stride, frame_to_key, key_idx, bc, t_frames, k_frames, hw, cfg_scale, dt,
             alpha, beta, dsigma, euler, (float*)out_main, (float*)out_edit);
+    WVD_CHECK_CUDA(cudaGetLastError());
+    return WVD_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_tile_blend(void* values, void* weight, const void* tile, int planes, int H, int W,
+                                                                     int th, int tw, int y0, int x0, int bounds, int border_h,
+                                                                     int border_w, int dtype, wvd_stream_t stream) {
+    WVD_REQUIRE(dtype == WVD_BF16 || dtype == WVD_F32, "wvd_tile_blend: bad dtype %d", dtype);
+    WVD_REQUIRE(values && weight && tile, "wvd_tile_blend: null pointer");
+    WVD_REQUIRE(planes > 0 && H > 0 && W > 0 && th > 0 && tw > 0 && y0 >= 0 && x0 >= 0 && y0 + th <= H && x0 + tw <= W,
+                "wvd_tile_blend: the tile (%d x %d at %d, %d) does not fit the %d x %d plane", th, tw, y0, x0, H, W);
+    WVD_REQUIRE(bounds >= 0 && bounds < 16 && border_h >= 0 && border_w >= 0, "wvd_tile_blend: bad bounds / border");
+    WVD_REQUIRE(((bounds & 3) == 3 || border_h > 0) && ((bounds & 12) == 12 || border_w > 0),
+                "wvd_tile_blend: a side that is not a volume boundary needs a positive border width");
+    const int ve = dtype == WVD_BF16 ? 8 : 4;
+    WVD_REQUIRE((long long)planes * th * tw < (1ll << 31), "wvd_tile_blend: tile too large (planes * th * tw must be < 2^31)");
+    const bool vec = tw % ve == 0 && x0 % ve == 0 && W % ve == 0 && aligned16(values) && aligned16(weight) && aligned16(tile);
+    const long long total = (long long)planes * th * (vec ? tw / ve : tw);
+    const unsigned grid = ew::stream_grid(total, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define WVD_TB(T, V) ew::tile_blend_kernel<T, V><<<grid, 256, 0, st>>>((T*)values, (T*)weight, (const T*)tile, planes, H, W, th, tw, y0, x0, bounds, border_h, border_w)
+    if (dtype == WVD_BF16) { if (vec) WVD_TB(__nv_bfloat16, 8); else WVD_TB(__nv_bfloat16, 1); }
+    else { if (vec) WVD_TB(float, 4); else WVD_TB(float, 1); }
+#undef WVD_TB
+    WVD_CHECK_CUDA(cudaGetLastError());
+    return WVD_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int wvd_tile_finalize(void* values, const void* weight, int planes, int64_t hw, int clamp,
+                                                                        float lo, float hi, int dtype, wvd_stream_t stream) {
+    WVD_REQUIRE(dtype == WVD_BF16 || dtype == WVD_F32, "wvd_tile_finalize: bad dtype %d", dtype);
+    WVD_REQUIRE(values && weight && planes > 0 && hw > 0, "wvd_tile_finalize: bad arguments");
+    const int ve = dtype == WVD_BF16 ? 8 : 4;
+    const bool vec = hw % ve == 0 && aligned16(values) && aligned16(weight);
+    const long long total = (long long)planes * (vec ? hw / ve : hw);
+    const unsigned grid = ew::stream_grid(total, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define WVD_TF(T, V) ew::tile_finalize_kernel<T, V><<<grid, 256, 0, st>>>((T*)values, (const T*)weight, planes, hw, clamp, lo, hi)
+    if (dtype == WVD_BF16) { if (vec) WVD_TF(__nv_bfloat16, 8); else WVD_TF(__nv_bfloat16, 1); }
+    else { if (vec) WVD_TF(float, 4); else WVD_TF(float, 1); }
+#undef WVD_TF
     WVD_CHECK_CUDA(cudaGetLastError());
     return WVD_OK;
 }

@@ -467,3 +467,32 @@ def editor_step(z_main: Tensor, z_edit: Tensor, v_posi, v_nega, frame_to_key: Te
                                       float(dsigma), 1 if euler else 0, out_main.data_ptr(), out_edit.data_ptr(), _dt(z_main),
                                       _stream()), "wvd_editor_step")
     return out_main, out_edit
+
+
+def tile_blend(values: Tensor, weight: Tensor, tile: Tensor, y0: int, x0: int, is_bound, border_width) -> None:
+    """values[:, :, :, y0:y0+th, x0:x0+tw] += tile * mask ; weight[y0:.., x0:..] += mask  (wan_video_vae.py:1081-1152).
+    values (1, C, T, H, W), tile (1, C, T, th, tw), weight (H, W); is_bound = (top, bottom, left, right) volume boundaries,
+    border_width = (rows, columns) of the linear ramp on the other sides."""
+    if values.dim() != 5 or tile.dim() != 5 or values.shape[0] != 1 or tile.shape[:3] != values.shape[:3]:
+        raise WvdError(f"tile_blend: values (1, C, T, H, W) and tile (1, C, T, th, tw) expected, got {tuple(values.shape)} / {tuple(tile.shape)}")
+    for name, x in (("values", values), ("weight", weight), ("tile", tile)):
+        if not x.is_cuda or not x.is_contiguous() or x.dtype != values.dtype:
+            raise WvdError(f"tile_blend: {name} must be a contiguous CUDA tensor of the values' dtype (there is no CPU fallback)")
+    _, c, t, h, w = values.shape
+    th, tw = tile.shape[3], tile.shape[4]
+    if tuple(weight.shape) != (h, w):
+        raise WvdError(f"tile_blend: weight must be the ({h}, {w}) plane, got {tuple(weight.shape)}")
+    bounds = sum(1 << i for i, b in enumerate(is_bound) if b)
+    check(_lib.load().wvd_tile_blend(values.data_ptr(), weight.data_ptr(), tile.data_ptr(), c * t, h, w, th, tw, int(y0), int(x0),
+                                     bounds, int(border_width[0]), int(border_width[1]), _dt(values), _stream()), "wvd_tile_blend")
+
+
+def tile_finalize(values: Tensor, weight: Tensor, clamp: Optional[Tuple[float, float]] = None) -> Tensor:
+    """values / weight in place (weight broadcast over channels and frames), optionally clamped (wan_video_vae.py:1151-1153)."""
+    if not values.is_cuda or not values.is_contiguous() or not weight.is_contiguous() or weight.dtype != values.dtype:
+        raise WvdError("tile_finalize: contiguous CUDA tensors of one dtype expected")
+    _, c, t, h, w = values.shape
+    lo, hi = clamp if clamp is not None else (0.0, 0.0)
+    check(_lib.load().wvd_tile_finalize(values.data_ptr(), weight.data_ptr(), c * t, h * w, 1 if clamp is not None else 0,
+                                        float(lo), float(hi), _dt(values), _stream()), "wvd_tile_finalize")
+    return values
