@@ -174,13 +174,13 @@ def t5_block_forward(block: T5SelfAttention, x: Tensor, key_mask: Optional[Tenso
         return t
 
     h = buf("h", (n, d))
-    ops.qk_rmsnorm_rope(x, None, _w(block.norm1, dt, dev), None, block.norm1.eps, q_out=h)
+    ops.qk_rmsnorm_rope(x, None, _w(block.norm1, dt, dev), None, engine._unwrap(block.norm1).eps, q_out=h)
     qkv = buf("qkv", (n, 3 * da))
     ops.linear_grouped(h, [_w(at.q, dt, dev), _w(at.k, dt, dev), _w(at.v, dt, dev)], [None, None, None], out=qkv)
     a = ops.attention_bias(qkv[:, :da], qkv[:, da:2 * da], qkv[:, 2 * da:], at.num_heads, bias, key_mask, 1.0,
                            out=buf("attn", (n, da)))
     ops.linear(a, _w(at.o, dt, dev), None, ops.EPI_BIAS_RES, residual=x, out=x)                 # x + attn(norm1(x))
-    ops.qk_rmsnorm_rope(x, None, _w(block.norm2, dt, dev), None, block.norm2.eps, q_out=h)
+    ops.qk_rmsnorm_rope(x, None, _w(block.norm2, dt, dev), None, engine._unwrap(block.norm2).eps, q_out=h)
     g = ops.linear(h, _w(ff.gate[0], dt, dev), None, ops.EPI_BIAS_GELU_T5, out=buf("gate", (n, ff.dim_ffn)))
     u = ops.linear(h, _w(ff.fc1, dt, dev), None, ops.EPI_BIAS_MUL, residual=g, out=buf("mid", (n, ff.dim_ffn)))
     ops.linear(u, _w(ff.fc2, dt, dev), None, ops.EPI_BIAS_RES, residual=x, out=x)                # x + ffn(norm2(x))
@@ -218,14 +218,15 @@ class WanTextEncoder(nn.Module):
             raise NotImplementedError("(B, L1, L2) attention masks are not on the wvd path (the pipeline passes (B, L))")
         outs = []
         for i in range(b):
-            x = emb(ids[i]).to(dtype=dt).contiguous()                       # (L, dim) gather
+            table = emb.weight if emb.weight.device == dev else emb.weight.to(dev)      # offloaded by a vram wrapper
+            x = torch.nn.functional.embedding(ids[i], table).to(dtype=dt).contiguous()  # (L, dim) gather
             km = None if mask is None else (mask[i] != 0).to(torch.int32).contiguous()
             shared = self.pos_embedding.table(l, l, dt, dev) if self.shared_pos else None
             for block in self.blocks:
-                bias = shared if self.shared_pos else block.pos_embedding.table(l, l, dt, dev)
+                bias = shared if self.shared_pos else engine._unwrap(block.pos_embedding).table(l, l, dt, dev)
                 t5_block_forward(block, x, km, bias, self._ws, ops)
             out = torch.empty_like(x)
-            ops.qk_rmsnorm_rope(x, None, _w(self.norm, dt, dev), None, self.norm.eps, q_out=out)
+            ops.qk_rmsnorm_rope(x, None, _w(self.norm, dt, dev), None, engine._unwrap(self.norm).eps, q_out=out)
             outs.append(out)
         return torch.stack(outs, dim=0)
 
