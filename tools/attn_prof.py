@@ -1,9 +1,11 @@
 """Developer tool: per-phase cycle counters of one attention CTA (see wvd_debug_attention_profile).
 Needs a library built with WVD_NVCC_FLAGS=-DWVD_ATTN_PROF python -m video_styler_b200.build --force."""
 import os, sys
+import ctypes
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from video_styler_b200 import _lib, ops
+_lib.load().wvd_debug_attention_profile.argtypes = [ctypes.c_void_p]      # a bare int would be truncated to 32 bits
 
 n, h = int(os.environ.get("N", 29640)), int(os.environ.get("H", 40))
 q = torch.randn(n, 3 * h * 128, device="cuda").bfloat16()
