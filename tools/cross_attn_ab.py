@@ -34,17 +34,18 @@ def sdpa():
 
 contenders = [("one_tile(2 CTA/SM)", lambda: ops.attention(q, k, v, h, out=out, kernel=_lib.ATTN_ONE_TILE)),
               ("two_tile", lambda: ops.attention(q, k, v, h, out=out, kernel=_lib.ATTN_TWO_TILE)),
+              ("cg2_persistent", lambda: ops.attention(q, k, v, h, out=out, kernel=_lib.ATTN_CG2_PERSISTENT)),
               ("torch sdpa", sdpa)]
 ref = sdpa()[0].transpose(0, 1).reshape(a.sq, d).float()
-for name, fn in contenders[:2]:
+for name, fn in contenders[:3]:
     fn()
     torch.cuda.synchronize()
     err = float((out.float() - ref).norm() / ref.norm())
     print(f"{name}: relL2 vs sdpa {err:.2e}  timeouts {_lib.debug_flags()['timeouts']}")
 fl = 4.0 * a.sq * a.sk * h * 128
-for rnd in range(3):
+for rnd in range(4):
     line = []
-    for name, fn in contenders[rnd % 3:] + contenders[:rnd % 3]:
+    for name, fn in contenders[rnd % 4:] + contenders[:rnd % 4]:
         for _ in range(5):
             fn()
         flush.zero_()

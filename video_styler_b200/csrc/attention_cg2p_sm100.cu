@@ -13,15 +13,16 @@
 // resident and walks a list of work items; the pipeline never drains:
 //   * K/V loads, S buffers, P hand-overs and PV/QK^T issue run over ONE global sequence of KV steps G = item * n_kv + j;
 //     ring-slot load L carries K of step L and V of step L-2 across item boundaries (the heads may differ);
-//   * Q is double-buffered: Q of item k+1 is loaded in the middle of item k;
+//   * Q is triple-buffered: Q of item k+1 is requested at the start of item k (its buffer was last used, as Q and as
+//     output staging, by item k-2), so even the 4-step items of the 512-key cross-attention get their Q a whole item ahead;
 //   * QK^T of the first two steps of item k+1 is issued during the last two steps of item k, so S(k+1, 0) is waiting when
 //     the softmax warps come back from the epilogue of item k;
 //   * the epilogue of item k (TMEM -> bf16 -> the dead Q buffer of item k as staging -> 128-byte row segments to global)
 //     runs on the softmax warps while the tensor core already works on item k+1; the first PV of item k+1 (which
 //     overwrites O) waits for one "O drained" barrier per item.
 // Work items are dealt round-robin (item = cluster + k * clusters, head-major so that concurrently running items share
-// K/V in L2); all items cost the same.  For short key sequences (n_kv < 8: two steps ahead would cross more than one item
-// boundary) the same kernel runs with one item per CTA pair, i.e. as the non-persistent kernel.
+// K/V in L2); all items cost the same.  For very short key sequences (n_kv < 4: two steps ahead would cross more than one
+// item boundary) the same kernel runs with one item per CTA pair, i.e. as the non-persistent kernel.
 // Only the LEADER CTA (cluster rank 0) issues MMAs.  Both CTAs' TMA loads complete on the leader's barriers
 // (cp.async.bulk.tensor .cta_group::2), both CTAs' softmax warps hand P over on the leader's barriers (remote arrive),
 // tcgen05.commit is multicast to the S-full / slot-free / PV-done / O-full barriers of both CTAs.
@@ -55,7 +56,8 @@ constexpr int SLOT_BYTES = KHALF_BYTES + VHALF_BYTES;      // 32 KB: (K_L, V_{L-
 #endif
 constexpr int SLOTS = WVD_CG2P_SLOTS;         // 5 also fits (232,320 of 232,448 bytes)
 static_assert(SLOTS <= 5, "barrier layout holds at most 5 ring slots");
-constexpr int QBUFS = 2;
+// shared memory: 3 Q buffers + 4 slots = 224 KB + barriers / exchange = 232,320 of the 232,448 bytes a CTA may have
+constexpr int QBUFS = 3;                      // Q(k+1) is requested at the START of item k: its buffer was last used by item k-2
 constexpr int SBUF = 3;                       // S buffers in TMEM
 constexpr int O_COL = SBUF * 128;             // first TMEM column of the O accumulator
 constexpr int SOFTMAX_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9;
@@ -63,7 +65,7 @@ constexpr int NUM_THREADS = 10 * 32;
 constexpr int BAR_BYTES = 384;
 constexpr int XCHG_BYTES = 3 * BQ * 4;        // m[row], l[warpgroup][row] fp32
 constexpr int SMEM_BYTES = QBUFS * Q_BYTES + SLOTS * SLOT_BYTES + BAR_BYTES + XCHG_BYTES + 1024;
-constexpr int MIN_KV_PERSISTENT = 8;
+constexpr int MIN_KV_PERSISTENT = 4;         // two steps ahead must cross at most ONE item boundary, and the Q prefetch needs >= 2 steps
 constexpr uint32_t IDESC_QK = make_idesc_bf16(256, 128, 0, 0);   // A = Q (K-major), B = K (K-major), M = 256 over the pair
 constexpr uint32_t IDESC_PV = make_idesc_bf16(256, 128, 0, 1);   // A = P (TMEM), B = V (MN-major)
 constexpr float REF_MARGIN = 8.0f;
@@ -89,9 +91,9 @@ attention_cg2p_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t kv_smem = smem_base + QBUFS * Q_BYTES;
     const uint32_t bar_base = kv_smem + SLOTS * SLOT_BYTES;
     auto q_full = [&](int qb) { return bar_base + qb * 8; };                     // LEADER: both CTAs' Q tiles have landed in buffer qb
-    auto q_free = [&](int qb) { return bar_base + 16 + qb * 8; };                // MINE: my 8 epilogue warps are done with buffer qb (Q reads + staging)
-    auto kv_full = [&](int s) { return bar_base + 32 + s * 8; };                 // LEADER: both halves of slot s have landed
-    auto kv_free = [&](int s) { return bar_base + 80 + s * 8; };                 // the MMAs reading slot s have completed
+    auto q_free = [&](int qb) { return bar_base + 24 + qb * 8; };                // MINE: my 8 epilogue warps are done with buffer qb (Q reads + staging)
+    auto kv_full = [&](int s) { return bar_base + 48 + s * 8; };                 // LEADER: both halves of slot s have landed
+    auto kv_free = [&](int s) { return bar_base + 88 + s * 8; };                 // the MMAs reading slot s have completed
     auto s_full = [&](int b) { return bar_base + 128 + b * 8; };                 // S buffer b holds Q K^T
     // LEADER: hand-over c of P of the step in S buffer b is in TMEM of BOTH CTAs.  Per BUFFER, not per warpgroup (parity
     // aliasing, see attention_cg2_sm100.cu).
@@ -162,13 +164,12 @@ attention_cg2p_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 if (rank != 0) mbar_arrive_cluster(lf);
             };
             load_q(0);
-            const int q_ahead_step = n_kv / 2;          // Q of the next item is requested at this step of the current one
             // load L carries my halves of (K of global step L, V of global step L-2) into ring slot L % SLOTS, one barrier
             int kk = 0, kj = 0;                          // item / step of global step L      (K part)
             int vk = 0, vj = -2;                         // item / step of global step L - 2  (V part)
             for (int L = 0; L <= total + 1; ++L) {
                 const bool has_k = L < total, has_v = L >= 2;
-                if (has_k && kj == q_ahead_step && kk + 1 < n_my) load_q(kk + 1);
+                if (has_k && kj == 0 && kk + 1 < n_my) load_q(kk + 1);       // a whole item ahead of its first QK^T
                 if (has_k || has_v) {
                     const int slot = L % SLOTS;
                     if (L >= SLOTS) mbar_wait(kv_free(slot), ((L / SLOTS) - 1) & 1, 0x110 + slot);
