@@ -253,3 +253,37 @@ def test_denoise_switches_are_bit_identical():
     finally:
         P.model_fn_wan_video = orig
     assert torch.equal(outs[0], outs[1])
+
+
+def test_engine_sends_v_first_when_the_exchange_asks_for_it(golden_dir):
+    """Ulysses fast path, host side: an exchange that exposes ``v_ready`` gets the v projection FIRST (its scatter then
+    overlaps the q | k projection); the block output is unchanged.  (The real peer-memory exchange needs GPUs; here a
+    recording stand-in checks the call order and that v is final when announced.)"""
+    fix = _load(golden_dir, "tiny_t2v")
+    dit, _ = build_models(fix)
+    cfg = O.DIT_CONFIGS[fix["size"]]
+    blk = dit.blocks[0]
+    g = torch.Generator().manual_seed(0)
+    n, d = 96, cfg["dim"]
+    x = torch.randn(n, d, generator=g)
+    ctx = torch.randn(16, d, generator=g)
+    t_mod = torch.randn(1, 6, d, generator=g)
+    rope = engine.RopeInfo(cpu_backend.make_rope_table(dit.freqs, "cpu"), (2, 6, 8))
+    ws = engine.workspace(n, d, cfg["ffn_dim"], 16, torch.float32, "cpu")
+    want = engine.dit_block_forward(blk, x.clone(), ctx, t_mod, rope, ws, cpu_backend).clone()
+
+    class Recording(engine.SelfAttnExchange):
+        world = 2                      # > 1: take the v-first branch (attention itself stays local in this stand-in)
+        events = []
+
+        def v_ready(self, ops, qkv, heads):
+            self.events.append(("v_ready", qkv[:, 2 * heads * 128:].clone()))
+
+        def norm_rope_attend(self, ops, qkv, heads, wq, wk, eps, rope, out, ws):
+            self.events.append(("attend", qkv[:, 2 * heads * 128:].clone()))
+            return super().norm_rope_attend(ops, qkv, heads, wq, wk, eps, rope, out, ws)
+    ex = Recording()
+    got = engine.dit_block_forward(blk, x.clone(), ctx, t_mod, rope, ws, cpu_backend, ex)
+    assert [e[0] for e in ex.events] == ["v_ready", "attend"]
+    assert torch.equal(ex.events[0][1], ex.events[1][1])          # v was final when it was announced
+    assert torch.allclose(got, want, rtol=0, atol=1e-6)
